@@ -1,0 +1,277 @@
+// Generic fp32 decoder evaluation (CUDA cores).  Handles every decoder topology the reference
+// can express after folding (any widths <= 512, any skip layout, CombinedDecoder with classifier
+// head, feature-mode queries).  The shipped 2 x 5-layer x 512 topology normally runs on the
+// tcgen05 kernel in k1_tc.cu; this kernel is the exact-fp32 path for everything else.
+//
+// Replaces, per chunk of points (SURVEY.md §2b K1/K1'):
+//   utils/mesh.py:24-63,82-115        grid construction + chunk loop + H2D/D2H
+//   utils/utils.py:376-430,561-572    kinematic_embedding + latent expand/cat
+//   networks/model.py:139-188,285-350 decoder forward
+//   utils/mesh.py:207-247             nonzero(sdf<0) bounding box (fused as atomics)
+#include "common.cuh"
+
+namespace asdf {
+namespace {
+
+constexpr int PT = 32;        // points per tile
+constexpr int PTS = 36;       // padded row stride (floats) of the k-major activation tiles
+constexpr int NT = 256;       // threads per block
+constexpr int MAXW = 512;     // widest layer supported
+
+struct SimtArgs {
+  asdf_simt_desc d;
+  asdf_query q;
+  const float* stat;
+  const float* samp;
+  const float* cls;
+  float* out_hand;
+  float* out_obj;
+  int32_t* out_cls;
+  int32_t* bbox;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// out[n][p] = relu( sum_k WxT[k][n] in[k][p] + sum_d MB[n][d] u[d][p] + MB[n][D] )
+__device__ void hidden_layer(const float* __restrict__ wxt, const float* __restrict__ mb,
+                             int h, int n, int npad, int has_m, int D,
+                             const float* __restrict__ in, const float* __restrict__ u,
+                             float* __restrict__ out) {
+  const int tn = threadIdx.x & 63;
+  const int p0 = (threadIdx.x >> 6) * 8;
+  float acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int nn = tn + 64 * j;
+    const float b = nn < npad ? __ldg(mb + (size_t)nn * (D + 1) + D) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j][i] = b;
+  }
+  if (has_m) {
+    for (int dd = 0; dd < D; ++dd) {
+      const float4 ua = ld4(u + dd * PTS + p0), ub = ld4(u + dd * PTS + p0 + 4);
+      const float x[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int nn = tn + 64 * j;
+        const float w = nn < npad ? __ldg(mb + (size_t)nn * (D + 1) + dd) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(w, x[i], acc[j][i]);
+      }
+    }
+  }
+  const int jmax = (npad - tn + 63) / 64;   // number of live feature slots of this thread
+#pragma unroll 2
+  for (int k = 0; k < h; ++k) {
+    const float4 xa = ld4(in + k * PTS + p0), xb = ld4(in + k * PTS + p0 + 4);
+    const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float* wr = wxt + (size_t)k * npad + tn;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < jmax) {
+        const float w = __ldg(wr + 64 * j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(w, x[i], acc[j][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int nn = tn + 64 * j;
+    if (nn < n) {
+      float4 a = make_float4(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f), fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
+      float4 b = make_float4(fmaxf(acc[j][4], 0.f), fmaxf(acc[j][5], 0.f), fmaxf(acc[j][6], 0.f), fmaxf(acc[j][7], 0.f));
+      *reinterpret_cast<float4*>(out + nn * PTS + p0) = a;
+      *reinterpret_cast<float4*>(out + nn * PTS + p0 + 4) = b;
+    }
+  }
+}
+
+// Small-width head: y[o][p] = sum_k W[k*ldw + o] in[k][p] (+ M u + B), one warp per 4 points.
+// Result (before any activation) is left in res[o*PT + p].
+__device__ void small_head(const float* __restrict__ wxt, int ldw, const float* __restrict__ mb,
+                           int h, int n, int has_m, int D, const float* __restrict__ in,
+                           const float* __restrict__ u, float* __restrict__ res) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = 0; o < n; ++o) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < h; k += 32) {
+      const float w = __ldg(wxt + (size_t)k * ldw + o);
+      const float4 x = ld4(in + k * PTS + warp * 4);
+      s[0] = fmaf(w, x.x, s[0]); s[1] = fmaf(w, x.y, s[1]);
+      s[2] = fmaf(w, x.z, s[2]); s[3] = fmaf(w, x.w, s[3]);
+    }
+    if (has_m) {
+      for (int dd = lane; dd < D; dd += 32) {
+        const float w = __ldg(mb + (size_t)o * (D + 1) + dd);
+        const float4 x = ld4(u + dd * PTS + warp * 4);
+        s[0] = fmaf(w, x.x, s[0]); s[1] = fmaf(w, x.y, s[1]);
+        s[2] = fmaf(w, x.z, s[2]); s[3] = fmaf(w, x.w, s[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+    }
+    if (lane == 0) {
+      const float b = mb ? __ldg(mb + (size_t)o * (D + 1) + D) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) res[o * PT + warp * 4 + i] = s[i] + b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* act0 = smem;
+  float* act1 = act0 + MAXW * PTS;
+  float* u = act1 + MAXW * PTS;                       // [ASDF_MAX_POINT_DIM][PTS]
+  float* res = u + ASDF_MAX_POINT_DIM * PTS;          // [8][PT] head outputs
+  float* sdf = res + 8 * PT;                          // [2][PT]
+  int* cls_s = reinterpret_cast<int*>(sdf + 2 * PT);  // [PT]
+
+  const asdf_simt_desc& d = a.d;
+  const asdf_query& q = a.q;
+  const int64_t total = q.end - q.begin;
+  const int64_t n_tiles = (total + PT - 1) / PT;
+  const int L = d.n_layers;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = q.begin + tile * PT;
+    for (int b = 0; b < d.n_branches; ++b) {
+      const int D = d.point_dim[b];
+      __syncthreads();
+      // ---- per-point input vector u[d][p]
+      if (threadIdx.x < PT) {
+        const int p = threadIdx.x;
+        const int64_t i = base + p;
+        if (i < q.end) {
+          if (q.mode == ASDF_QUERY_POINTS) {
+            const float* row = q.points_dev + (size_t)i * q.point_stride;
+            for (int dd = 0; dd < D; ++dd) u[dd * PTS + p] = __ldg(row + d.point_index[b][dd]);
+          } else {
+            float x0, x1, x2;
+            grid_point(i, q.N, q.mode, q.voxel, q.origin[0], q.origin[1], q.origin[2], x0, x1, x2);
+            u[0 * PTS + p] = x0; u[1 * PTS + p] = x1; u[2 * PTS + p] = x2;
+          }
+        } else {
+          for (int dd = 0; dd < D; ++dd) u[dd * PTS + p] = 0.f;
+        }
+      }
+      __syncthreads();
+      float* in = act0;
+      float* out = act1;
+      for (int l = 0; l < L - 1; ++l) {
+        const int32_t* t = d.table[b][l];
+        hidden_layer(a.stat + t[4], a.samp + t[5], t[0], t[1], t[2], t[3], D, in, u, out);
+        __syncthreads();
+        float* tmp = in; in = out; out = tmp;
+      }
+      const int32_t* t = d.table[b][L - 1];
+      small_head(a.stat + t[4], t[2], a.samp + t[5], t[0], t[1], t[3], D, in, u, res);
+      if (d.n_class > 0 && b == 0) {
+        __syncthreads();
+        if (threadIdx.x < PT) {     // stash the sdf head before res is reused for the logits
+          for (int o = 0; o < t[1]; ++o) sdf[o * PT + threadIdx.x] = res[o * PT + threadIdx.x];
+        }
+        __syncthreads();
+        // classifier weights: [n_class][h+1] row-major -> treat as ldw=1 per class
+        for (int c = 0; c < d.n_class; ++c)
+          small_head(a.cls + (size_t)c * (t[0] + 1), 1, nullptr, t[0], 1, 0, 0, in, u, res + c * PT);
+        __syncthreads();
+        if (threadIdx.x < PT) {
+          int best = 0;
+          float bv = res[threadIdx.x] + __ldg(a.cls + t[0]);
+          for (int c = 1; c < d.n_class; ++c) {
+            const float v = res[c * PT + threadIdx.x] + __ldg(a.cls + (size_t)c * (t[0] + 1) + t[0]);
+            if (v > bv) { bv = v; best = c; }
+          }
+          cls_s[threadIdx.x] = best;
+          for (int o = 0; o < t[1]; ++o) res[o * PT + threadIdx.x] = sdf[o * PT + threadIdx.x];
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < PT) {
+        const int p = threadIdx.x;
+        for (int o = 0; o < t[1]; ++o) {
+          float v = res[o * PT + p];
+          if (d.pre_tanh) v = tanhf(v);
+          v = tanhf(v);
+          sdf[(d.n_branches == 2 ? b : o) * PT + p] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < PT) {
+      const int p = threadIdx.x;
+      const int64_t i = base + p;
+      const bool live = i < q.end;
+      const bool two = d.n_branches == 2 || d.n_outputs == 2;
+      float vh = 1.f, vo = 1.f;
+      if (live) {
+        vh = sdf[p];
+        a.out_hand[i - q.begin] = vh;
+        if (two) { vo = sdf[PT + p]; if (a.out_obj) a.out_obj[i - q.begin] = vo; }
+        if (a.out_cls) a.out_cls[i - q.begin] = d.n_class > 0 ? cls_s[p] : 0;
+      }
+      if (a.bbox && q.mode != ASDF_QUERY_POINTS) {
+        if (q.bbox_mask & 1) bbox_update(a.bbox, live && vh < 0.f, i, q.N);
+        if (q.bbox_mask & 2) bbox_update(a.bbox + 6, live && two && vo < 0.f, i, q.N);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace asdf
+
+extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev,
+                              const float* sample_dev, const float* cls_dev, const asdf_query* q,
+                              float* out_hand_dev, float* out_obj_dev, int32_t* out_cls_dev,
+                              int32_t* bbox_dev, void* stream) {
+  using namespace asdf;
+  ASDF_REQUIRE(desc && q && static_dev && sample_dev && out_hand_dev, "asdf_simt_eval: null argument");
+  ASDF_REQUIRE(desc->n_branches == 1 || desc->n_branches == 2, "n_branches must be 1 or 2");
+  ASDF_REQUIRE(desc->n_layers >= 2 && desc->n_layers <= ASDF_MAX_LAYERS, "bad n_layers %d", desc->n_layers);
+  ASDF_REQUIRE(desc->n_outputs >= 1 && desc->n_outputs <= 2, "n_outputs must be 1 or 2");
+  ASDF_REQUIRE(desc->n_class >= 0 && desc->n_class <= 8, "n_class must be in [0,8]");
+  ASDF_REQUIRE(desc->n_class == 0 || cls_dev, "classifier weights missing");
+  ASDF_REQUIRE(q->end >= q->begin, "empty or negative query range");
+  for (int b = 0; b < desc->n_branches; ++b) {
+    ASDF_REQUIRE(desc->point_dim[b] >= 1 && desc->point_dim[b] <= ASDF_MAX_POINT_DIM, "bad point_dim");
+    for (int l = 0; l < desc->n_layers; ++l) {
+      const int32_t* t = desc->table[b][l];
+      ASDF_REQUIRE(t[0] >= 0 && t[0] <= MAXW && t[2] >= t[1] && t[2] <= MAXW && t[2] % 8 == 0,
+                   "layer %d of branch %d: widths (h=%d n=%d npad=%d) outside the supported range", l, b, t[0], t[1], t[2]);
+      if (l < desc->n_layers - 1) ASDF_REQUIRE(l == 0 ? t[0] == 0 : t[0] > 0, "layer %d: bad input width", l);
+    }
+    ASDF_REQUIRE(desc->table[b][desc->n_layers - 1][1] == desc->n_outputs, "last layer width != n_outputs");
+  }
+  if (q->mode == ASDF_QUERY_POINTS) {
+    ASDF_REQUIRE(q->points_dev && q->point_stride >= 1, "points query without points");
+  } else {
+    ASDF_REQUIRE(q->mode == ASDF_QUERY_GRID_REFERENCE || q->mode == ASDF_QUERY_GRID_REGULAR, "bad query mode");
+    ASDF_REQUIRE(q->N >= 2 && q->end <= (int64_t)q->N * q->N * q->N && q->begin >= 0, "grid range outside N^3");
+    ASDF_REQUIRE(desc->point_dim[0] == 3 && (desc->n_branches == 1 || desc->point_dim[1] == 3),
+                 "grid queries need xyz-folded weights (point_dim 3)");
+  }
+  if (q->end == q->begin) return ASDF_OK;
+  SimtArgs a;
+  a.d = *desc; a.q = *q; a.stat = static_dev; a.samp = sample_dev; a.cls = cls_dev;
+  a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.out_cls = out_cls_dev; a.bbox = bbox_dev;
+  const size_t smem = (size_t)(2 * MAXW * PTS + ASDF_MAX_POINT_DIM * PTS + 8 * PT + 2 * PT + PT) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    ASDF_CUDA_CHECK(cudaFuncSetAttribute(simt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  ASDF_CUDA_CHECK(cudaGetDevice(&dev));
+  ASDF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = (q->end - q->begin + PT - 1) / PT;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  simt_eval_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+  ASDF_CUDA_CHECK(cudaGetLastError());
+  return ASDF_OK;
+}

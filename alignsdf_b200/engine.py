@@ -1,0 +1,255 @@
+"""Host-side driver of the CUDA library: packs a decoder once, binds a sample
+(latent + poses) and launches grid / point evaluations and marching cubes.
+
+Everything numeric happens in libalignsdf_b200.so; this module only folds
+weights (packer.py), owns device buffers (torch tensors) and marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib, packer
+from ._lib import AsdfError
+
+INT_MAX = 2 ** 31 - 1
+_GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
+
+
+def _device_of(latent, device=None):
+    if device is not None and str(device) not in ("cpu",):
+        d = torch.device(device)
+        if d.type == "cuda":
+            return d
+    if isinstance(latent, torch.Tensor) and latent.is_cuda:
+        return latent.device
+    if not torch.cuda.is_available():
+        raise AsdfError("alignsdf_b200 needs a CUDA device (B200); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class BoundSample:
+    """A decoder with one sample's latent/pose folded in, ready to be queried."""
+
+    def __init__(self, engine, branches, feature_mode):
+        self.engine = engine
+        self.feature_mode = feature_mode
+        self.device = engine.device
+        topo = engine.topo
+        pack = packer.pack_simt(branches)
+        self.simt_pack = pack
+        dev = self.device
+        if engine.simt_static is None:      # static weights do not depend on the sample
+            engine.simt_static = torch.from_numpy(pack.static).to(dev)
+        self.simt_sample = torch.from_numpy(pack.sample).to(dev, non_blocking=True)
+        d = _lib.SimtDesc()
+        d.n_branches, d.n_layers, d.n_outputs = pack.n_branches, pack.n_layers, pack.n_outputs
+        d.pre_tanh = int(topo.pre_tanh)
+        d.n_class = 0 if topo.classifier is None else int(topo.classifier[0].shape[0])
+        for b in range(pack.n_branches):
+            d.point_dim[b] = int(pack.point_dim[b])
+            idx = (packer.branch_feature_index(topo, topo.branches[b][0]) if feature_mode
+                   else np.arange(3))
+            for k, v in enumerate(idx):
+                d.point_index[b][k] = int(v)
+            for l in range(pack.n_layers):
+                for k in range(6):
+                    d.table[b][l][k] = int(pack.table[b, l, k])
+        self.simt_desc = d
+        self.tc = None
+        if not feature_mode and engine.tc_supported:
+            from . import tc_pack
+            self.tc = tc_pack.bind(engine, branches)
+
+    # ------------------------------------------------------------------
+    def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str):
+        dev = self.device
+        hand = torch.empty(n, dtype=torch.float32, device=dev)
+        two = self.simt_desc.n_branches == 2 or self.simt_desc.n_outputs == 2
+        obj = torch.empty(n, dtype=torch.float32, device=dev) if two else None
+        cls = torch.empty(n, dtype=torch.int32, device=dev) if want_cls else None
+        box = None
+        if bbox:
+            box = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3,
+                               dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        use_tc = self.tc is not None and not want_cls and path in ("auto", "tc")
+        if path == "tc" and not use_tc:
+            raise AsdfError("tensor-core path requested but not available for this decoder/query")
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            if use_tc:
+                rc = L.asdf_tc_eval(C.byref(self.tc.desc), _lib.ptr(self.engine.tc_static),
+                                    _lib.ptr(self.tc.sample), C.byref(q), _lib.ptr(hand),
+                                    _lib.ptr(obj), _lib.ptr(box), st)
+                _lib.check(rc, "asdf_tc_eval")
+            else:
+                rc = L.asdf_simt_eval(C.byref(self.simt_desc), _lib.ptr(self.engine.simt_static),
+                                      _lib.ptr(self.simt_sample), _lib.ptr(self.engine.cls_dev),
+                                      C.byref(q), _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(cls),
+                                      _lib.ptr(box), st)
+                _lib.check(rc, "asdf_simt_eval")
+        return hand, obj, cls, box
+
+    def eval_grid(self, N, voxel, origin, mode="reference", begin=0, end=None, bbox_mask=0,
+                  want_cls=False, path=None):
+        """Evaluate linear grid indices [begin,end) -> (hand, obj, cls, bbox int32[12] or None)."""
+        if self.feature_mode:
+            raise AsdfError("grid evaluation needs an xyz-folded sample (feature_mode=False)")
+        end = N ** 3 if end is None else end
+        q = _lib.Query()
+        q.mode, q.N, q.begin, q.end = _GRID_MODES[mode], int(N), int(begin), int(end)
+        q.voxel = float(voxel)
+        for k in range(3):
+            q.origin[k] = float(origin[k])
+        q.points_dev, q.point_stride, q.bbox_mask = None, 0, int(bbox_mask)
+        return self._run(q, end - begin, want_cls, bbox_mask != 0, path or self.engine.path)
+
+    def eval_points(self, points: torch.Tensor, want_cls=False, path=None):
+        """points: CUDA f32 [P, stride]; xyz rows, or embedded feature rows in feature mode."""
+        _lib.require_cuda(points, "points")
+        pts = points.to(torch.float32).contiguous()
+        q = _lib.Query()
+        q.mode, q.N, q.begin, q.end = _lib.QUERY_POINTS, 0, 0, int(pts.shape[0])
+        q.voxel = 0.0
+        q.points_dev, q.point_stride, q.bbox_mask = pts.data_ptr(), int(pts.shape[1]), 0
+        hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, path or self.engine.path)
+        return hand, obj, cls
+
+
+class DecoderEngine:
+    """Per-decoder state: topology, static weights resident in HBM."""
+
+    def __init__(self, decoder, device):
+        self.device = torch.device(device)
+        self.topo = packer.decoder_topology(decoder)
+        self.simt_static = None
+        self.cls_dev = None
+        if self.topo.classifier is not None:
+            Wc, bc = self.topo.classifier
+            self.cls_dev = torch.from_numpy(
+                np.concatenate([Wc, bc[:, None]], 1).astype(np.float32)).to(self.device)
+        self.path = os.environ.get("ALIGNSDF_B200_PATH", "auto")
+        self.tc_static = None
+        self.tc_supported = False
+        try:
+            from . import tc_pack
+            self.tc_supported = tc_pack.supported(self.topo) and _lib.lib().asdf_tc_static_bytes() > 0
+            if self.tc_supported:
+                self.tc_static = tc_pack.pack_static(self)
+        except ImportError:
+            self.tc_supported = False
+
+    def bind(self, latent, specs, mano_results, obj_results, feature_mode=False) -> BoundSample:
+        branches = packer.fold_decoder(self.topo, latent, specs, mano_results, obj_results, feature_mode)
+        return BoundSample(self, branches, feature_mode)
+
+
+def unwrap_decoder(decoder):
+    """Legacy API: accept a thin adapter around a decoder (e.g. one that returns only the first
+    output); the weights are taken from the first sub-module that owns ``lin*`` layers."""
+    for m in decoder.modules():
+        if any(n.startswith("lin") for n, _ in m.named_children()):
+            return m
+    return decoder
+
+
+_ENGINES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _version_of(decoder):
+    return tuple(int(p._version) for p in decoder.parameters())
+
+
+def get_engine(decoder, device) -> DecoderEngine:
+    """Cached engine per (decoder object, device); rebuilt if any parameter was modified."""
+    device = torch.device(device)
+    per = _ENGINES.setdefault(decoder, {})
+    ver = _version_of(decoder)
+    hit = per.get(device)
+    if hit is None or hit[0] != ver:
+        hit = (ver, DecoderEngine(decoder, device))
+        per[device] = hit
+    return hit[1]
+
+
+# ----------------------------------------------------------------------------
+# marching cubes
+# ----------------------------------------------------------------------------
+def _decode_ordered(bits: int) -> float:
+    b = bits if bits >= 0 else bits ^ 0x7FFFFFFF
+    return float(np.array([b], np.int32).view(np.float32)[0])
+
+
+def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
+                   index0_offset=0, want_keys=False):
+    """GPU marching cubes.  vol: CUDA f32 [n0,n1,n2].  Returns dict of CUDA tensors
+    verts [V,3] (array-axis order x spacing), points [V,3] (= origin + verts), faces [F,3] int32,
+    keys [V] int64 (when want_keys).  Raises ValueError like skimage when level is outside the
+    data range (the reference catches it, utils/mesh.py:353-358)."""
+    _lib.require_cuda(vol, "vol")
+    vol = vol.to(torch.float32).contiguous()
+    if vol.dim() != 3:
+        raise ValueError("Input volume should be a 3D numpy array.")
+    p = _lib.McParams()
+    p.n0, p.n1, p.n2 = (int(s) for s in vol.shape)
+    p.full1, p.full2 = p.n1, p.n2
+    p.index0_offset = int(index0_offset)
+    p.iso = float(level)
+    for k in range(3):
+        p.spacing[k] = float(spacing[k])
+        p.origin[k] = float(origin[k])
+    L = _lib.lib()
+    dev = vol.device
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        scratch = torch.empty(L.asdf_mc_scratch_bytes(C.byref(p)), dtype=torch.uint8, device=dev)
+        totals = torch.empty(4, dtype=torch.int64, device=dev)
+        _lib.check(L.asdf_mc_count(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(totals), st),
+                   "asdf_mc_count")
+        nv, nt, mn, mx = (int(x) for x in totals.cpu())
+        if not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
+            raise ValueError("Surface level must be within volume data range.")
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        points = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
+        keys = torch.empty(nv, dtype=torch.int64, device=dev) if want_keys else None
+        if nv > 0 or nt > 0:
+            _lib.check(L.asdf_mc_emit(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(verts),
+                                      _lib.ptr(points), _lib.ptr(faces), _lib.ptr(keys), st),
+                       "asdf_mc_emit")
+    return dict(verts=verts, points=points, faces=faces, keys=keys)
+
+
+def grid_points(N, voxel, origin, mode="reference", begin=0, end=None, device=None) -> torch.Tensor:
+    """Query coordinates of linear indices [begin,end) as the kernels generate them."""
+    dev = _device_of(None, device)
+    end = N ** 3 if end is None else end
+    q = _lib.Query()
+    q.mode, q.N, q.begin, q.end = _GRID_MODES[mode], int(N), int(begin), int(end)
+    q.voxel = float(voxel)
+    for k in range(3):
+        q.origin[k] = float(origin[k])
+    out = torch.empty((end - begin, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().asdf_grid_points(C.byref(q), _lib.ptr(out), _lib.stream_ptr(dev)),
+                   "asdf_grid_points")
+    return out
+
+
+def embed_points(xyz: torch.Tensor, specs, mano_results, obj_results) -> torch.Tensor:
+    """features[P,pf] = A.xyz + c on the GPU (public kinematic_embedding API)."""
+    _lib.require_cuda(xyz, "xyz")
+    A, c = packer.embedding_affine(specs, mano_results, obj_results)
+    aff = torch.from_numpy(np.concatenate([A, c[:, None]], 1).astype(np.float32)).to(xyz.device)
+    x = xyz.to(torch.float32).contiguous()
+    out = torch.empty((x.shape[0], A.shape[0]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().asdf_embed_points(_lib.ptr(x), x.shape[0], _lib.ptr(aff), A.shape[0],
+                                                _lib.ptr(out), _lib.stream_ptr(x.device)),
+                   "asdf_embed_points")
+    return out

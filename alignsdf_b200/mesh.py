@@ -1,0 +1,204 @@
+"""Drop-in for the reference's ``utils/mesh.py`` (same function names, argument order
+and side effects), backed by the CUDA library.
+
+    create_mesh_combined_decoder   <-> utils/mesh.py:17-195
+    get_higher_res_cube            <-> utils/mesh.py:198-256
+    convert_sdf_samples_to_ply     <-> utils/mesh.py:331-399
+    write_verts_label_to_npz       <-> utils/mesh.py:281-297
+
+Differences, all additive: the functions accept CUDA tensors and keep volumes on the
+device; ``create_mesh_combined_decoder`` additionally *returns* the meshes (the reference
+returns None and only writes files); ``grid_mode="regular"`` selects the intended
+(unsheared) lattice, the default reproduces the reference's lattice bit for bit.
+``eval_mode=True`` (ICP against ground-truth meshes on disk, deep_sdf/metrics) is outside
+the hot path and raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from .trimesh_lite import Mesh, split as _split
+
+INT_MAX = 2 ** 31 - 1
+
+
+def _bbox_to_minmax(box, hand_branch, obj_branch):
+    """int32[12] device bbox -> (min_index, max_index) f32 tensors with the reference's
+    conventions: an empty branch contributes (0,0,0)/(0,0,0) (utils/mesh.py:209-211,225-227)
+    and the two branches are merged with elementwise min / max (:239-247)."""
+    b = box.cpu().tolist()
+    mins, maxs = [], []
+    for use, o in ((hand_branch, 0), (obj_branch, 6)):
+        if not use:
+            continue
+        if b[o + 3] < 0:
+            mins.append(torch.zeros(3)); maxs.append(torch.zeros(3))
+        else:
+            mins.append(torch.tensor(b[o:o + 3], dtype=torch.float32))
+            maxs.append(torch.tensor(b[o + 3:o + 6], dtype=torch.float32))
+    if len(mins) == 1:
+        return mins[0], maxs[0]
+    return torch.min(mins[0], mins[1]), torch.max(maxs[0], maxs[1])
+
+
+def _regrid(min_index, max_index, N, voxel_size):
+    """utils/mesh.py:249-254, same f32 arithmetic on 4 scalars."""
+    new_cube_size = (torch.max(max_index - min_index) + 4) * voxel_size
+    new_voxel_size = new_cube_size / (N - 1)
+    new_origin = (min_index - 2) * voxel_size - 1.0
+    return new_voxel_size, new_origin
+
+
+def get_higher_res_cube(hand_branch, obj_branch, sdf_values_hand, sdf_values_obj, N, voxel_origin,
+                        voxel_size):
+    """Same contract as the reference; volumes may live on the GPU (the reduction then runs there
+    as part of the evaluation kernels; for externally supplied volumes a torch reduction is used)."""
+    mins, maxs = [], []
+    for use, vol in ((hand_branch, sdf_values_hand), (obj_branch, sdf_values_obj)):
+        if not use:
+            continue
+        idx = torch.nonzero(vol < 0)
+        if idx.shape[0] == 0:
+            mins.append(torch.zeros(3)); maxs.append(torch.zeros(3))
+        else:
+            mins.append(idx.min(0).values.float().cpu()); maxs.append(idx.max(0).values.float().cpu())
+    mn = mins[0] if len(mins) == 1 else torch.min(mins[0], mins[1])
+    mx = maxs[0] if len(maxs) == 1 else torch.max(maxs[0], maxs[1])
+    return _regrid(mn, mx, N, voxel_size)
+
+
+def _as_float_list(x):
+    if isinstance(x, torch.Tensor):
+        return [float(v) for v in x.reshape(-1).tolist()]
+    return [float(v.item() if isinstance(v, torch.Tensor) else v) for v in x]
+
+
+def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_size, ply_filename_out,
+                               offset=None, scale=None, eval_mode=False, task='obman',
+                               return_mesh=False):
+    """Marching cubes (GPU) -> origin shift -> optional scale/offset -> largest watertight
+    component if the mesh splits -> PLY.  Returns (verts, faces, trans, scale) like the reference
+    (raw marching-cubes vertices, i.e. before the origin shift and the component filter)."""
+    if eval_mode:
+        raise NotImplementedError("eval_mode (ICP against ground-truth meshes) is outside the hot "
+                                  "path (SURVEY.md §2 #9)")
+    vol = pytorch_3d_sdf_tensor
+    if not isinstance(vol, torch.Tensor):
+        vol = torch.as_tensor(np.asarray(vol))
+    if not vol.is_cuda:
+        vol = vol.to(torch.device("cuda", torch.cuda.current_device()))
+    vs = float(voxel_size.item() if isinstance(voxel_size, torch.Tensor) else voxel_size)
+    origin = _as_float_list(voxel_grid_origin)
+    try:
+        out = _engine.marching_cubes(vol, level=0.0, spacing=[vs] * 3, origin=origin)
+        if out["faces"].shape[0] == 0:
+            raise RuntimeError("No surface found at the given iso value.")
+    except (ValueError, RuntimeError) as e:
+        logging.warning("Cannot reconstruct mesh from '{}'".format(ply_filename_out))
+        print(e)
+        res = (None, None, np.array([0, 0, 0]), np.array([1]))
+        return res + (None,) if return_mesh else res
+    verts = out["verts"].cpu().numpy()
+    faces = out["faces"].cpu().numpy()
+    mesh_points = out["points"].cpu().numpy()              # origin + verts (f32), :360-363
+    if scale is not None:
+        mesh_points = mesh_points * scale
+    if offset is not None:
+        mesh_points = mesh_points + offset
+    source_mesh = Mesh(mesh_points, faces, process=False)
+    pieces = _split(source_mesh)                           # watertight components, :372
+    if len(pieces) > 1:
+        max_area, final_mesh = -1, pieces[0]
+        for per_mesh in pieces:
+            a = per_mesh.area
+            if a > max_area:
+                max_area, final_mesh = a, per_mesh
+        source_mesh = final_mesh
+    source_mesh.export(ply_filename_out)
+    res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
+    return res + (source_mesh,) if return_mesh else res
+
+
+def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_filename_out,
+                             offset=None, scale=None):
+    pts = pytorch_3d_xyz_tensor.data.cpu().numpy()
+    labels = pytorch_label_tensor.cpu().numpy()
+    if scale is not None:
+        pts = pts * scale
+    if offset is not None:
+        pts = pts + offset
+    np.savez(npz_filename_out, points=pts, labels=labels)
+
+
+def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
+                obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None):
+    """The two evaluation passes of utils/mesh.py:24-120 on the GPU.
+
+    Returns dict(pass1_hand, pass1_obj, hand, obj, cls, voxel (0-dim f32 tensor),
+    origin (f32[3] tensor), bound) with [N,N,N] CUDA volumes."""
+    dev = _engine._device_of(latent_vec, device)
+    eng = _engine.get_engine(decoder, dev)
+    bound = eng.bind(latent_vec, specs, mano_results, obj_results)
+    voxel_size = 2.0 / (N - 1)
+    mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
+    if mask == 0:
+        raise ValueError("at least one of hand_branch / obj_branch must be set")
+    h1, o1, _, box = bound.eval_grid(N, voxel_size, [-1.0, -1.0, -1.0], grid_mode, bbox_mask=mask,
+                                     path=path)
+    mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
+    new_voxel_size, new_origin = _regrid(mn, mx, N, voxel_size)
+    h2, o2, c2, _ = bound.eval_grid(N, float(new_voxel_size), new_origin.tolist(), grid_mode,
+                                    want_cls=cls_branch and eng.topo.classifier is not None, path=path)
+    shp = (N, N, N)
+    return dict(pass1_hand=h1.view(shp), pass1_obj=None if o1 is None else o1.view(shp),
+                hand=h2.view(shp), obj=None if o2 is None else o2.view(shp),
+                cls=None if c2 is None else c2.view(shp), voxel=new_voxel_size, origin=new_origin,
+                min_index=mn, max_index=mx, bound=bound)
+
+
+def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,
+                                 obj_results, cam_intr, specs, filename, N=256, max_batch=32 ** 3,
+                                 offset=None, scale=None, device="cpu", label_out=False, viz=False,
+                                 eval_mode=False, task='obman', grid_mode="reference"):
+    """Same call as the reference (``max_batch`` is accepted and ignored: the whole grid is one
+    launch).  Writes ``<filename>_hand.ply`` / ``_obj.ply`` (and ``_hand_label.npz`` with
+    ``label_out``) and returns ``{"hand": mesh or None, "obj": mesh or None}``."""
+    ply_filename_hand = filename + "_hand"
+    ply_filename_obj = filename + "_obj"
+    decoder.eval()
+    vols = sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch,
+                       obj_branch, cls_branch, None if device == "cpu" else device, grid_mode)
+    voxel_size = vols["voxel"]
+    voxel_origin = vols["origin"].tolist()
+    result = {"hand": None, "obj": None}
+    if hand_branch:
+        vertices, mesh_faces, offset, scale, mesh = convert_sdf_samples_to_ply(
+            vols["hand"], voxel_origin, voxel_size, ply_filename_hand + ".ply", None, None, eval_mode,
+            task, return_mesh=True)
+        result["hand"] = mesh
+        if label_out and (vertices is not None):
+            # utils/mesh.py:137-184: re-query the decoder at the marching-cubes vertices
+            v = torch.from_numpy(vertices).clone()
+            for k in range(3):
+                v[:, k] = voxel_origin[k] + v[:, k]
+            bound = vols["bound"]
+            if bound.engine.topo.classifier is None:
+                raise IndexError("label_out needs a decoder with a classifier head "
+                                 "(the reference fails the same way, utils/mesh.py:157)")
+            _, _, cls = bound.eval_points(v.to(bound.device), want_cls=True)
+            out_labels = cls.float().cpu()
+            if viz:
+                logging.warning("viz outputs (_label.obj, _color.ply) are not produced by alignsdf_b200")
+            write_verts_label_to_npz(v, out_labels, ply_filename_hand + "_label.npz", offset, scale)
+    if obj_branch:
+        # the object mesh reuses the HAND call's offset/scale (utils/mesh.py:186-194)
+        *_, mesh = convert_sdf_samples_to_ply(vols["obj"], voxel_origin, voxel_size,
+                                              ply_filename_obj + ".ply", offset, scale, False,
+                                              return_mesh=True)
+        result["obj"] = mesh
+    return result

@@ -86,8 +86,8 @@ def decoder_topology(decoder) -> Topology:
     n_layers = len(next(iter(layers.values())))
     if n_layers < 2 or n_layers > ASDF_MAX_LAYERS:
         raise ValueError(f"unsupported number of linear layers: {n_layers}")
-    pf = int(getattr(decoder, "point_feat_size"))
-    style = str(getattr(decoder, "encode_style"))
+    pf = int(getattr(decoder, "point_feat_size", 3))          # plain DeepSDF decoders: xyz only
+    style = str(getattr(decoder, "encode_style", "nerf"))
     if separate:
         d0_hand = layers["linh"][0][0].shape[1]
         sub = {"nerf": pf, "hand": pf, "obj": 3, "both": pf - 3}[style]
@@ -217,8 +217,11 @@ def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
     out = []
     for tag, prefix in topo.branches:
         idx = branch_feature_index(topo, tag)
-        A, c = A_full[idx], c_full[idx]
         nf = len(idx)
+        if feature_mode:        # u = this branch's own slice of the embedded features
+            A, c = np.eye(nf), np.zeros(nf)
+        else:
+            A, c = A_full[idx], c_full[idx]
         folded = []
         for l, (W, b) in enumerate(topo.layers[prefix]):
             d0 = L + nf

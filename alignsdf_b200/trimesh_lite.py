@@ -1,0 +1,94 @@
+"""Minimal stand-in for the two trimesh features the hot path uses.
+
+The reference builds ``trimesh.Trimesh(vertices, faces, process=False)``, calls
+``trimesh.graph.split`` and ``mesh.export(path)`` (utils/mesh.py:371-397).  trimesh
+is not installable here, so this module provides the same surface; when trimesh
+*is* importable, ``to_trimesh`` hands back a real ``trimesh.Trimesh``.
+
+Host-side post-processing only (the reference does this on the CPU as well);
+moving it to the GPU is a "next" row.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Mesh:
+    def __init__(self, vertices, faces, process=False):
+        self.vertices = np.asarray(vertices)
+        self.faces = np.asarray(faces).reshape(-1, 3)
+
+    @property
+    def area_faces(self):
+        v = self.vertices.astype(np.float64)
+        a, b, c = (v[self.faces[:, i]] for i in range(3))
+        return 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
+
+    @property
+    def area(self):
+        return float(self.area_faces.sum())
+
+    @property
+    def is_watertight(self):
+        if len(self.faces) < 4:
+            return False
+        e = np.sort(np.concatenate([self.faces[:, [0, 1]], self.faces[:, [1, 2]], self.faces[:, [2, 0]]]), 1)
+        _, counts = np.unique(e, axis=0, return_counts=True)
+        return bool(np.all(counts == 2))
+
+    def export(self, path):
+        export_ply(path, self.vertices, self.faces)
+
+    def to_trimesh(self):
+        try:
+            import trimesh
+        except ImportError:
+            return self
+        return trimesh.Trimesh(vertices=self.vertices, faces=self.faces, process=False)
+
+
+def export_ply(path, vertices, faces):
+    """Binary little-endian PLY with float32 vertices and ``list uchar int`` faces (the layout
+    trimesh's exporter and the legacy plyfile writer of deep_sdf/mesh.py:95-112 both produce)."""
+    v = np.ascontiguousarray(vertices, dtype="<f4").reshape(-1, 3)
+    f = np.ascontiguousarray(faces, dtype="<i4").reshape(-1, 3)
+    header = ("ply\nformat binary_little_endian 1.0\n"
+              f"element vertex {len(v)}\nproperty float x\nproperty float y\nproperty float z\n"
+              f"element face {len(f)}\nproperty list uchar int vertex_indices\nend_header\n")
+    rec = np.empty(len(f), dtype=[("n", "u1"), ("idx", "<i4", (3,))])
+    rec["n"] = 3
+    rec["idx"] = f
+    with open(path, "wb") as fh:
+        fh.write(header.encode("ascii"))
+        fh.write(v.tobytes())
+        fh.write(rec.tobytes())
+
+
+def split(mesh: Mesh, only_watertight=True):
+    """Connected components over faces sharing an edge, as sub-meshes (trimesh.graph.split)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    faces = mesh.faces
+    F = len(faces)
+    if F == 0:
+        return []
+    e = np.sort(np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]), 1).astype(np.int64)
+    fid = np.tile(np.arange(F), 3)
+    key = e[:, 0] * (int(faces.max()) + 1) + e[:, 1]
+    order = np.argsort(key, kind="stable")
+    key, fid = key[order], fid[order]
+    uniq, start, counts = np.unique(key, return_index=True, return_counts=True)
+    two = start[counts == 2]                       # edges shared by exactly two faces
+    adj = coo_matrix((np.ones(len(two)), (fid[two], fid[two + 1])), shape=(F, F))
+    n, labels = connected_components(adj, directed=False)
+    edge_count_of = counts[np.searchsorted(uniq, key)]
+    out = []
+    for c in range(n):
+        sel = np.nonzero(labels == c)[0]
+        if only_watertight:
+            if len(sel) < 4 or not np.all(edge_count_of[labels[fid] == c] == 2):
+                continue
+        sub = faces[sel]
+        used, inv = np.unique(sub, return_inverse=True)
+        out.append(Mesh(mesh.vertices[used], inv.reshape(-1, 3).astype(faces.dtype)))
+    return out

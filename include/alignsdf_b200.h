@@ -1,0 +1,132 @@
+/* alignsdf_b200 -- C ABI of the B200-native AlignSDF reconstruction hot path.
+ *
+ * The reference has no FFI layer: its hot path is plain Python calling ATen
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds instead
+ * (ctypes stub in INTEGRATION.md); every entry point names the reference code it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - every pointer named *_dev is a DEVICE pointer owned by the caller (a torch
+ *    tensor); the library never frees or retains it beyond the call;
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it;
+ *  - return value 0 = OK, negative = error; asdf_last_error() returns the message
+ *    of the last failure on the calling thread;
+ *  - no hidden global state; no CPU fallback: if no CUDA device is usable the
+ *    calls fail with ASDF_ERR_CUDA.
+ */
+#ifndef ALIGNSDF_B200_H_
+#define ALIGNSDF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASDF_ABI_VERSION 1
+#define ASDF_MAX_LAYERS 8
+#define ASDF_MAX_POINT_DIM 64
+
+#define ASDF_OK 0
+#define ASDF_ERR_ARG (-1)
+#define ASDF_ERR_CUDA (-2)
+#define ASDF_ERR_UNSUPPORTED (-3)
+
+/* Query set.  Replaces the CPU grid construction + per-chunk H2D copy of
+ * utils/mesh.py:24-48,82-96 (deep_sdf/mesh.py:21-46). */
+#define ASDF_QUERY_GRID_REFERENCE 0 /* sheared lattice the reference really evaluates (true division) */
+#define ASDF_QUERY_GRID_REGULAR 1   /* floor-division lattice */
+#define ASDF_QUERY_POINTS 2         /* explicit rows of `point_stride` floats */
+typedef struct {
+  int32_t mode;
+  int32_t N;             /* grid resolution (grid modes) */
+  int64_t begin, end;    /* linear index range [begin,end) of the N^3 grid, or [0,P) for points */
+  float voxel;           /* grid spacing  */
+  float origin[3];       /* column k of the query uses origin[k] */
+  const float* points_dev; /* ASDF_QUERY_POINTS: [P, point_stride] */
+  int32_t point_stride;
+  int32_t bbox_mask;     /* bit0: hand field feeds the bbox, bit1: object field */
+} asdf_query;
+
+/* Generic fp32 decoder description (any widths <= 512, any skip layout).
+ * Replaces networks/model.py:79-188 (CombinedDecoder.forward) and :285-350
+ * (SeparateDecoder.forward) together with utils/utils.py:376-430 (kinematic_embedding)
+ * and :561-572 (decode_sdf_multi_output) after host-side folding (alignsdf_b200/packer.py). */
+typedef struct {
+  int32_t n_branches;                       /* 2: separate hand/object MLPs, 1: one MLP with n_outputs */
+  int32_t n_layers;                         /* linear layers per branch */
+  int32_t n_outputs;                        /* width of the last layer (1 or 2) */
+  int32_t pre_tanh;                         /* NetworkSpecs.use_tanh */
+  int32_t n_class;                          /* classifier logits on the penultimate activations, 0 = none */
+  int32_t point_dim[2];                     /* D per branch: 3 (xyz) or the branch's feature count */
+  int32_t point_index[2][ASDF_MAX_POINT_DIM]; /* column of the query row feeding u[d] */
+  int32_t table[2][ASDF_MAX_LAYERS][6];     /* h, n, npad, has_M, off_static, off_sample (in floats) */
+} asdf_simt_desc;
+
+/* y_l = relu(WxT_l^T x + M_l u + B_l) ... tanh;   static_dev: WxT blocks, sample_dev: [npad][D+1] blocks,
+ * cls_dev: [n_class][h_last+1] (weights then bias) or NULL.
+ * out_hand_dev / out_obj_dev: [end-begin] f32.  out_cls_dev: [end-begin] int32 argmax or NULL.
+ * bbox_dev: int32[12] = hand {min0,min1,min2,max0,max1,max2} then object {...}, updated with
+ * atomicMin/Max over the unravelled indices of every point whose field is < 0
+ * (utils/mesh.py:198-247); the caller initialises it to {INT_MAX x3, -1 x3} x2.  May be NULL. */
+int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev, const float* sample_dev,
+                   const float* cls_dev, const asdf_query* q, float* out_hand_dev, float* out_obj_dev,
+                   int32_t* out_cls_dev, int32_t* bbox_dev, void* stream);
+
+/* Tensor-core path for the shipped topology (two 5-layer 512-wide MLPs, skip at layer 2,
+ * utils/mesh.py:46-63,96-115 hot loops): tcgen05 / TMEM, fp16 x3 split precision. */
+typedef struct {
+  int32_t h[2];            /* width of layer 1 per branch (512 - d0), <= 256 */
+  float act_scale;         /* power of two applied to activations before the fp16 split */
+  float w_scale[2][3];     /* power of two applied to the weights of layers 1..3, per branch */
+  int64_t branch_stride;   /* bytes between the two branches' packed weight streams */
+} asdf_tc_desc;
+int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* sample_dev,
+                 const asdf_query* q, float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev,
+                 void* stream);
+/* Bytes of the packed static stream / floats of the per-sample block the tcgen05 path expects. */
+int64_t asdf_tc_static_bytes(void);
+int64_t asdf_tc_sample_floats(void);
+
+/* Query coordinates only (tests / debugging): xyz_dev [end-begin,3], bit-exact w.r.t. the
+ * reference's torch expressions at utils/mesh.py:32-40,86-94. */
+int asdf_grid_points(const asdf_query* q, float* xyz_dev, void* stream);
+
+/* Pose-align embedding as an affine map: feats[P,pf] = xyz[P,3] A^T + c.
+ * Replaces utils/utils.py:376-430 for the public kinematic_embedding() API. */
+int asdf_embed_points(const float* xyz_dev, int64_t P, const float* affine_dev /* [pf][4] */,
+                      int32_t pf, float* feats_dev, void* stream);
+
+/* Marching cubes over a [n0,n1,n2] f32 field.  Replaces the
+ * skimage.measure.marching_cubes_lewiner call at utils/mesh.py:354 / deep_sdf/mesh.py:81
+ * plus the vertex affine of utils/mesh.py:360-369. */
+typedef struct {
+  int32_t n0, n1, n2;      /* local volume (a z-slab including its halo plane) */
+  int32_t full1, full2;    /* extents of axes 1,2 of the full grid (== n1,n2) */
+  int64_t index0_offset;   /* global axis-0 index of local plane 0 (vertex keys and coordinates) */
+  float iso;
+  double spacing[3];
+  float origin[3];         /* points = origin + verts (utils/mesh.py:360-363) */
+} asdf_mc_params;
+size_t asdf_mc_scratch_bytes(const asdf_mc_params* p);
+/* Pass 1: classify + count + scan.  totals_dev: int64[4] = {n_verts, n_tris, min_bits, max_bits}
+ * (field min/max as ordered-int bit patterns, for the "level outside data range" check). */
+int asdf_mc_count(const float* vol_dev, const asdf_mc_params* p, void* scratch_dev,
+                  int64_t* totals_dev, void* stream);
+/* Pass 2: emit.  verts_dev [V,3] f32 (array-axis order * spacing, what marching_cubes returns),
+ * points_dev [V,3] f32 (origin + verts) or NULL, faces_dev [F,3] int32,
+ * keys_dev [V] uint64 global vertex keys (for slab stitching) or NULL. */
+int asdf_mc_emit(const float* vol_dev, const asdf_mc_params* p, const void* scratch_dev,
+                 float* verts_dev, float* points_dev, int32_t* faces_dev, uint64_t* keys_dev,
+                 void* stream);
+
+int asdf_abi_version(void);
+const char* asdf_last_error(void);
+/* 1 if a CUDA device with compute capability 10.x is present, else 0 (never falls back). */
+int asdf_device_ok(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNSDF_B200_H_ */

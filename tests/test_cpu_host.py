@@ -1,0 +1,194 @@
+"""CPU-side tests: oracle vs the reference's golden vectors, host logic, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from alignsdf_b200 import packer, synthetic, trimesh_lite
+from oracle import alignsdf_oracle as orc
+from oracle import mc_oracle as mo
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", helpers.field_cases())
+def test_synthetic_generator_is_bit_reproducible(name):
+    meta, g, dec, sample = helpers.load_case(name)
+    assert synthetic.state_digest(dec) == meta["digest"]
+
+
+@pytest.mark.parametrize("name", helpers.field_cases())
+def test_oracle_matches_reference_golden(name):
+    """oracle/alignsdf_oracle.py vs outputs captured from the real reference (tol 1e-6)."""
+    meta, g, dec, sample = helpers.load_case(name)
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs,
+                             sample.mano_results, sample.obj_results, meta["N"],
+                             meta.get("hand_branch", True), meta.get("obj_branch", True))
+    assert np.float32(float(res["voxel"])) == g["new_voxel"]
+    assert np.array_equal(res["origin"].numpy(), g["new_origin"])
+    for key, arr in (("pass1_hand", res["pass1_hand"]), ("pass1_obj", res["pass1_obj"]),
+                     ("pass2_hand", res["hand"]), ("pass2_obj", res["obj"])):
+        if key in g:
+            assert np.abs(arr.numpy() - g[key]).max() <= 1e-6, key
+    if "pass2_cls" in g:
+        assert np.array_equal(res["cls"].numpy().reshape(-1).astype(np.int32), g["pass2_cls"])
+    if "xyz2" in g:
+        xyz = orc.grid_points(meta["N"], torch.tensor(g["new_voxel"]), torch.tensor(g["new_origin"]))
+        assert np.array_equal(xyz.numpy(), g["xyz2"])
+
+
+def test_oracle_grid_above_2_pow_24():
+    g = np.load(os.path.join(helpers.GOLD, "grid512_windows.npz"))
+    for key in g.files:
+        _, a, b = key.split("_")
+        got = orc.grid_points(512, 2.0 / 511, [-1, -1, -1], "reference", int(a), int(b)).numpy()
+        assert np.array_equal(got, g[key])
+    # the shear really is there: axis 1 picks up z/N
+    p = orc.grid_points(512, 1.0, [0, 0, 0], "reference", 5 * 512 + 7, 5 * 512 + 8)[0]
+    assert p[2] == 7 and abs(float(p[1]) - (5 + 7 / 512)) < 1e-5
+    r = orc.grid_points(512, 1.0, [0, 0, 0], "regular", 5 * 512 + 7, 5 * 512 + 8)[0]
+    assert r.tolist() == [0.0, 5.0, 7.0]
+
+
+@pytest.mark.parametrize("name", helpers.field_cases())
+def test_folded_network_matches_reference_golden(name):
+    """packer.fold_decoder (latent -> bias, pose-align -> [out,3]) vs the reference (tol 1e-6)."""
+    meta, g, dec, sample = helpers.load_case(name)
+    topo = packer.decoder_topology(dec)
+    br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
+    N = meta["N"]
+    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
+    out = packer.folded_forward_numpy(br, xyz, topo.pre_tanh)
+    hand, obj = (out[0][:, 0], out[1][:, 0]) if topo.kind == "separate" else (out[0][:, 0], out[0][:, 1])
+    if "pass1_hand" in g:
+        assert np.abs(hand - g["pass1_hand"].reshape(-1)).max() <= 1e-6
+    if "pass1_obj" in g:
+        assert np.abs(obj - g["pass1_obj"].reshape(-1)).max() <= 1e-6
+
+
+def test_feature_mode_fold_matches_oracle():
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    topo = packer.decoder_topology(dec)
+    xyz = orc.grid_points(8, 2.0 / 7, [-1, -1, -1])
+    feats = orc.embed(xyz, sample.specs, sample.mano_results, sample.obj_results)
+    br = packer.fold_decoder(topo, sample.latent, sample.specs, None, None, feature_mode=True)
+    outs = []
+    for b, (tag, _) in zip(br, topo.branches):
+        idx = packer.branch_feature_index(topo, tag)
+        outs.append(packer.folded_forward_numpy([b], feats.numpy()[:, idx])[0][:, 0])
+    sd = dec.state_dict()
+    h, o, _ = orc.decode_points(sd, orc.decoder_cfg(dec), sample.latent, xyz, sample.specs,
+                                sample.mano_results, sample.obj_results)
+    assert np.abs(outs[0] - h[:, 0].detach().numpy()).max() <= 1e-6
+    assert np.abs(outs[1] - o[:, 0].detach().numpy()).max() <= 1e-6
+
+
+def test_embedding_affine_matches_explicit_embedding():
+    for pf, style in ((9, "both"), (51, "hand"), (6, "hand"), (6, "obj"), (54, "both")):
+        s = synthetic.make_sample(3, 256, pf, style)
+        xyz = torch.rand(64, 3) * 2 - 1
+        ref = orc.kinematic_embedding(xyz, s.mano_results, pf, s.specs["SdfScaleFactor"], s.obj_results, style)
+        got = packer.embed_points_torch(xyz, s)
+        assert torch.abs(ref - got).max() < 5e-6
+
+
+def test_non_rigid_pose_is_rejected():
+    s = synthetic.make_sample(0)
+    s.obj_results["obj_trans"][0, 3, 0] = 0.1            # projective row -> w != 1
+    with pytest.raises(ValueError, match="not affine"):
+        packer.embedding_affine(s.specs, s.mano_results, s.obj_results)
+
+
+def test_unsupported_variants_raise():
+    s = synthetic.make_sample(0, 256, 9, "both")
+    specs = dict(s.specs, PixelAlign=True)
+    dec = synthetic.make_decoder(0)
+    topo = packer.decoder_topology(dec)
+    with pytest.raises(NotImplementedError):
+        packer.fold_decoder(topo, s.latent, specs, s.mano_results, s.obj_results)
+    with pytest.raises(NotImplementedError):
+        packer.embedding_affine(dict(s.specs, PointFeatSize=9, EncodeStyle="nerf"), None, None)
+    with pytest.raises(AttributeError):
+        from alignsdf_b200.decoders import SeparateDecoder
+        SeparateDecoder(256, 9, "both", [512] * 4, use_classifier=True)
+
+
+def test_reference_style_state_dict_prefixes_are_accepted():
+    dec = synthetic.make_decoder(1)
+    sd = {"module.decoder." + k: v for k, v in dec.state_dict().items()}
+
+    class Holder:
+        point_feat_size, encode_style, latent_in = 9, "both", (2,)
+
+        def state_dict(self):
+            return sd
+    t = packer.decoder_topology(Holder())
+    assert t.kind == "separate" and t.latent_size == 256 and t.n_layers == 5
+
+
+def test_shared_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a GPU-less host and exports what include/*.h declares."""
+    from alignsdf_b200 import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "alignsdf_b200.h")).read()
+    declared = set(re.findall(r"\b(asdf_[a-z0-9_]+)\s*\(", header))
+    assert {"asdf_simt_eval", "asdf_tc_eval", "asdf_mc_count", "asdf_mc_emit", "asdf_grid_points"} <= declared
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.asdf_abi_version.restype = ctypes.c_int
+    assert lib.asdf_abi_version() == 1
+
+
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    """sizeof / offsetof as gcc sees include/alignsdf_b200.h == the ctypes mirrors in _lib.py."""
+    import subprocess
+    from alignsdf_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "alignsdf_b200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(asdf_query), sizeof(asdf_simt_desc),'
+        ' sizeof(asdf_tc_desc), sizeof(asdf_mc_params), offsetof(asdf_query, points_dev),'
+        ' offsetof(asdf_simt_desc, table), offsetof(asdf_mc_params, spacing), offsetof(asdf_tc_desc, branch_stride));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.Query), ctypes.sizeof(_lib.SimtDesc), ctypes.sizeof(_lib.TcDesc),
+            ctypes.sizeof(_lib.McParams), _lib.Query.points_dev.offset, _lib.SimtDesc.table.offset,
+            _lib.McParams.spacing.offset, _lib.TcDesc.branch_stride.offset]
+    assert got == want
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the GPU-less failure mode")
+def test_product_path_fails_loudly_without_gpu(tmp_path):
+    from alignsdf_b200 import mesh
+    from alignsdf_b200._lib import AsdfError
+    dec, s = synthetic.make_decoder(0), synthetic.make_sample(0)
+    with pytest.raises(AsdfError, match="no CPU path"):
+        mesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results,
+                                          s.obj_results, None, s.specs, str(tmp_path / "x"), N=8)
+
+
+def test_trimesh_lite_split_and_ply_roundtrip(tmp_path):
+    ax = np.linspace(-1, 1, 28, dtype=np.float32)
+    x, y, z = np.meshgrid(ax, ax, ax, indexing="ij")
+    two = np.minimum(np.sqrt((x + 0.45) ** 2 + y ** 2 + z ** 2) - 0.35,
+                     np.sqrt((x - 0.5) ** 2 + y ** 2 + z ** 2) - 0.22)
+    v, f, _ = mo.marching_cubes(two, 0.0)
+    m = trimesh_lite.Mesh(v, f)
+    parts = trimesh_lite.split(m)
+    assert len(parts) == 2 and all(p.is_watertight for p in parts)
+    big = max(parts, key=lambda p: p.area)
+    v2, f2 = mo.largest_component_if_split(v, f)
+    assert np.array_equal(big.vertices, v2) and np.array_equal(big.faces, f2)
+    path = str(tmp_path / "m.ply")
+    big.export(path)
+    rv, rf = mo.read_ply(path)
+    assert np.array_equal(rv, v2.astype(np.float32)) and np.array_equal(rf, f2)
+    open_mesh = trimesh_lite.Mesh(v, f[:-3])             # punch a hole: no longer watertight
+    assert len(trimesh_lite.split(open_mesh)) == 1

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the oracle and vs the reference's golden
+vectors.  Tolerance for SDF values: 1e-5 absolute (BASELINE.json north_star); grids, re-grid
+parameters, class labels, bounding boxes, marching-cubes output: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from alignsdf_b200 import engine, mesh as amesh, synthetic, utils as autils
+from alignsdf_b200.deep_sdf import mesh as legacy_mesh, utils as legacy_utils
+from oracle import alignsdf_oracle as orc
+from oracle import mc_oracle as mo
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+PATHS = ["simt", "auto"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda")
+
+
+def test_library_sees_a_blackwell_device(dev):
+    from alignsdf_b200 import _lib
+    assert _lib.lib().asdf_device_ok() == 1, _lib.lib().asdf_last_error()
+
+
+def test_grid_coordinates_bit_exact(dev):
+    meta, g, _, _ = helpers.load_case("sep_both9_n24")
+    got = engine.grid_points(24, float(g["new_voxel"]), g["new_origin"].tolist()).cpu().numpy()
+    assert np.array_equal(got, g["xyz2"])                       # captured from the real reference
+    w = np.load(os.path.join(helpers.GOLD, "grid512_windows.npz"))
+    for key in w.files:                                           # float(i) rounding above 2**24
+        _, a, b = key.split("_")
+        got = engine.grid_points(512, 2.0 / 511, [-1, -1, -1], "reference", int(a), int(b)).cpu().numpy()
+        assert np.array_equal(got, w[key]), key
+    reg = engine.grid_points(16, 2.0 / 15, [-1, -1, -1], "regular").cpu().numpy()
+    assert np.array_equal(reg, orc.grid_points(16, 2.0 / 15, [-1, -1, -1], "regular").numpy())
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", helpers.field_cases())
+def test_two_pass_fields_match_reference_golden(dev, name, path):
+    meta, g, dec, sample = helpers.load_case(name)
+    s = helpers.to_cuda(sample)
+    hb, ob = meta.get("hand_branch", True), meta.get("obj_branch", True)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob,
+                             cls_branch="pass2_cls" in g, path=path)
+    assert np.float32(float(vols["voxel"])) == g["new_voxel"]
+    assert np.array_equal(vols["origin"].numpy(), g["new_origin"])
+    for key, vol in (("pass1_hand", vols["pass1_hand"]), ("pass1_obj", vols["pass1_obj"]),
+                     ("pass2_hand", vols["hand"]), ("pass2_obj", vols["obj"])):
+        if key in g:
+            err = np.abs(vol.cpu().numpy() - g[key]).max()
+            assert err <= TOL, (key, err)
+    if "pass2_cls" in g:
+        assert np.array_equal(vols["cls"].cpu().numpy().reshape(-1), g["pass2_cls"])
+
+
+def test_slab_ranges_are_bit_identical_to_full_grid(dev):
+    """z-slab sharding property: evaluating [begin,end) pieces == evaluating the whole grid."""
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    bound = engine.get_engine(dec, dev).bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    N = 24
+    full_h, full_o, _, box = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3)
+    cuts = [0, 5 * N * N, 5 * N * N + 77, 17 * N * N, N ** 3]
+    hs, os_, boxes = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        h, o, _, bx = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], begin=a, end=b, bbox_mask=3)
+        hs.append(h); os_.append(o); boxes.append(bx)
+    assert torch.equal(torch.cat(hs), full_h) and torch.equal(torch.cat(os_), full_o)
+    bs = torch.stack(boxes).cpu()
+    merged = torch.cat([bs[:, 0:3].min(0).values, bs[:, 3:6].max(0).values,
+                        bs[:, 6:9].min(0).values, bs[:, 9:12].max(0).values])
+    assert torch.equal(merged, box.cpu())
+    # and the fused bbox equals nonzero(sdf<0) of the oracle-style reduction
+    idx = torch.nonzero(full_h.view(N, N, N) < 0)
+    assert box[0:3].tolist() == idx.min(0).values.tolist() and box[3:6].tolist() == idx.max(0).values.tolist()
+
+
+def test_empty_negative_set_follows_reference_convention(dev):
+    """No sdf<0 anywhere -> min=max=(0,0,0) (utils/mesh.py:209-211) -> cube of 4 voxels at -1-2vs."""
+    dec = synthetic.make_decoder(0)
+    with torch.no_grad():
+        dec.linh4.bias += 5.0
+        dec.lino4.bias += 5.0
+    s = helpers.to_cuda(synthetic.make_sample(0))
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, 12)
+    sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample_cpu(s).latent, s.specs,
+                             sample_cpu(s).mano_results, sample_cpu(s).obj_results, 12)
+    assert float(vols["voxel"]) == float(res["voxel"])
+    assert np.array_equal(vols["origin"].numpy(), res["origin"].numpy())
+
+
+def sample_cpu(s):
+    return s.to(torch.device("cpu"))
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_points_and_feature_queries_match_oracle(dev, path):
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    gen = torch.Generator().manual_seed(3)
+    xyz = torch.rand(1000, 3, generator=gen) * 2 - 1           # ragged size (not a tile multiple)
+    sd = dec.state_dict()
+    with torch.no_grad():
+        h, o, _ = orc.decode_points(sd, orc.decoder_cfg(dec), sample.latent, xyz, sample.specs,
+                                    sample.mano_results, sample.obj_results)
+    gh, go, _ = autils.decode_sdf_points(dec, s.latent, xyz.to(dev), s.mano_results, s.obj_results, s.specs)
+    assert (gh.cpu() - h[:, 0]).abs().max() <= TOL and (go.cpu() - o[:, 0]).abs().max() <= TOL
+    if path == "simt":
+        feats = autils.kinematic_embedding(xyz.to(dev), s.mano_results, xyz.shape[0], 9,
+                                           s.specs["SdfScaleFactor"], s.obj_results, "both")
+        ref_feats = orc.embed(xyz, sample.specs, sample.mano_results, sample.obj_results)
+        assert (feats.cpu() - ref_feats).abs().max() <= 5e-6
+        fh, fo, _ = autils.decode_sdf_multi_output(dec, s.latent, feats, s.mano_results, None, s.specs)
+        assert fh.shape == (1000, 1)
+        assert (fh[:, 0].cpu() - h[:, 0]).abs().max() <= TOL and (fo[:, 0].cpu() - o[:, 0]).abs().max() <= TOL
+    # empty query
+    eh, eo, _ = autils.decode_sdf_points(dec, s.latent, xyz[:0].to(dev), s.mano_results, s.obj_results, s.specs)
+    assert eh.numel() == 0 and eo.numel() == 0
+
+
+def test_torch_fp32_reference_forward_on_gpu(dev):
+    """Plain eager-PyTorch fp32 forward of the same module on the GPU vs the CUDA path."""
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    xyz = (torch.rand(4096, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(dev)
+    feats = autils.kinematic_embedding(xyz, s.mano_results, 4096, 9, s.specs["SdfScaleFactor"], s.obj_results, "both")
+    dgpu = synthetic.make_decoder(meta["seed"]).to(dev)
+    with torch.no_grad():
+        rh, ro, _ = dgpu(torch.cat([s.latent.expand(4096, -1), feats], 1))
+    gh, go, _ = autils.decode_sdf_points(dec, s.latent, xyz, s.mano_results, s.obj_results, s.specs)
+    assert (gh - rh[:, 0]).abs().max() <= TOL and (go - ro[:, 0]).abs().max() <= TOL
+
+
+def _mc_equal(vol, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+    v, f, k = mo.marching_cubes(vol, 0.0, spacing)
+    out = engine.marching_cubes(torch.from_numpy(np.ascontiguousarray(vol)).cuda(), 0.0, spacing, origin,
+                                want_keys=True)
+    assert np.array_equal(out["keys"].cpu().numpy().astype(np.uint64), k)
+    assert np.array_equal(out["faces"].cpu().numpy(), f)
+    gv = out["verts"].cpu().numpy()
+    assert np.array_equal(gv.view(np.uint32), v.view(np.uint32)), np.abs(gv - v).max()
+    pts = out["points"].cpu().numpy()
+    assert np.array_equal(pts, (np.asarray(origin, np.float32)[None] + v).astype(np.float32))
+    return v, f
+
+
+def test_marching_cubes_matches_oracle_bit_exact(dev):
+    rng = np.random.default_rng(0)
+    _mc_equal(rng.standard_normal((9, 10, 11)).astype(np.float32))            # every case + variant
+    _mc_equal(rng.standard_normal((33, 17, 40)).astype(np.float32), (0.5, 0.25, 2.0), (1.0, -2.0, 0.5))
+    ax = np.linspace(-1, 1, 48, dtype=np.float32)
+    x, y, z = np.meshgrid(ax, ax, ax, indexing="ij")
+    v, f = _mc_equal(np.sqrt(x * x + y * y + z * z) - np.float32(0.6), [2 / 47] * 3, [-1, -1, -1])
+    inv = mo.mesh_invariants(v, f)
+    assert inv["closed"] and inv["oriented"] and inv["euler"] == 2
+    tor = np.sqrt((np.sqrt(x * x + y * y) - 0.55) ** 2 + z * z) - np.float32(0.2)
+    v, f = _mc_equal(tor)
+    assert mo.mesh_invariants(v, f)["euler"] == 0
+    vol = np.ones((5, 5, 5), np.float32); vol[2, 2, 2] = 0.0                   # value == iso exactly
+    _mc_equal(vol - 0.0)
+
+
+def test_marching_cubes_level_outside_range(dev):
+    with pytest.raises(ValueError, match="Surface level must be within volume data range"):
+        engine.marching_cubes(torch.ones(6, 6, 6, device=dev), 0.0)
+
+
+def test_marching_cubes_slabs_stitch_to_the_single_gpu_mesh(dev):
+    meta, g, _, _ = helpers.load_case("sep_both9_n24")
+    vol = g["pass2_hand"]
+    full = engine.marching_cubes(torch.from_numpy(vol).cuda(), 0.0, [0.1] * 3, want_keys=True)
+    parts = []
+    for a, b in ((0, 9), (8, 17), (16, 24)):        # slabs with one halo plane each
+        parts.append(engine.marching_cubes(torch.from_numpy(np.ascontiguousarray(vol[a:b])).cuda(), 0.0,
+                                           [0.1] * 3, index0_offset=a, want_keys=True))
+    keys = torch.cat([p["keys"] for p in parts]).cpu().numpy()
+    verts = torch.cat([p["verts"] for p in parts]).cpu().numpy()
+    uk, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    off, faces = 0, []
+    for p in parts:
+        faces.append(inv[p["faces"].cpu().numpy().astype(np.int64) + off]); off += p["keys"].numel()
+    assert np.array_equal(uk, full["keys"].cpu().numpy())
+    assert np.array_equal(verts[first], full["verts"].cpu().numpy())
+    assert np.array_equal(np.concatenate(faces), full["faces"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["sep_both9_n24", "comb_cls_n12", "sep_both9_n32_handonly"])
+def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
+    """Public API: files written, meshes == oracle marching cubes of the GPU volumes."""
+    meta, g, dec, sample = helpers.load_case(name)
+    s = helpers.to_cuda(sample)
+    hb, ob = meta.get("hand_branch", True), meta.get("obj_branch", True)
+    label = "pass2_cls" in g
+    prefix = str(tmp_path / "img0")
+    res = amesh.create_mesh_combined_decoder(hb, ob, label, dec, s.latent, s.mano_results, s.obj_results,
+                                             None, s.specs, prefix, N=meta["N"], max_batch=2 ** 18,
+                                             label_out=label)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob)
+    vs = float(vols["voxel"]); org = vols["origin"].tolist()
+    for tag, use in (("hand", hb), ("obj", ob)):
+        path = f"{prefix}_{tag}.ply"
+        if not use:
+            assert not os.path.exists(path)
+            continue
+        vol = vols[tag].cpu().numpy()
+        if not (vol.min() <= 0 <= vol.max()):
+            assert res[tag] is None and not os.path.exists(path)
+            continue
+        v, f, _ = mo.marching_cubes(vol, 0.0, [vs] * 3)
+        pts = (np.asarray(org, np.float32)[None] + v).astype(np.float32)
+        if tag == "obj" and hb:
+            pts = pts * np.array([1]) + np.array([0, 0, 0])        # utils/mesh.py:366-369 with the hand's values
+        ev, ef = mo.largest_component_if_split(pts, f)
+        rv, rf = mo.read_ply(path)
+        assert np.array_equal(rf, ef) and np.array_equal(rv, ev.astype(np.float32))
+        assert np.array_equal(np.asarray(res[tag].faces), ef)
+    if label:
+        lab = np.load(prefix + "_hand_label.npz")
+        assert lab["points"].shape[0] == lab["labels"].shape[0] > 0
+        assert set(np.unique(lab["labels"])) <= set(range(6))
+
+
+def test_label_out_without_classifier_raises_like_reference(dev, tmp_path):
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    with pytest.raises(IndexError):
+        amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results, s.obj_results,
+                                           None, s.specs, str(tmp_path / "x"), N=16, label_out=True)
+
+
+def test_no_surface_is_not_an_error(dev, tmp_path, caplog):
+    dec = synthetic.make_decoder(0)
+    with torch.no_grad():
+        dec.linh4.bias += 5.0
+        dec.lino4.bias += 5.0
+    s = helpers.to_cuda(synthetic.make_sample(0))
+    res = amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results, s.obj_results,
+                                             None, s.specs, str(tmp_path / "none"), N=10)
+    assert res == {"hand": None, "obj": None}
+    assert "Cannot reconstruct mesh" in caplog.text
+    v = amesh.convert_sdf_samples_to_ply(torch.ones(8, 8, 8), [-1, -1, -1], 0.1, str(tmp_path / "n.ply"))
+    assert v[0] is None and v[1] is None and v[2].tolist() == [0, 0, 0] and v[3].tolist() == [1]
+
+
+def test_legacy_deep_sdf_api(dev, tmp_path):
+    meta = helpers.golden_index()["legacy_n16"]
+    g = np.load(os.path.join(helpers.GOLD, "legacy_n16.npz"))
+    dec = synthetic.make_decoder(meta["seed"], "combined", 256, 3, "nerf")
+    sample = synthetic.make_sample(meta["seed"], 256, 3, "nerf")
+
+    class FirstOutput(torch.nn.Module):                    # DeepSDF-style single-output adapter
+        def __init__(self, comb):
+            super().__init__(); self.comb = comb
+
+        def forward(self, x):
+            return self.comb(x)[0]
+    wrapped = FirstOutput(dec)
+    N = meta["N"]
+    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).to(dev)
+    sdf = legacy_utils.decode_sdf(wrapped, sample.latent.to(dev), xyz)
+    assert sdf.shape == (N ** 3, 1)
+    assert np.abs(sdf[:, 0].cpu().numpy().reshape(N, N, N) - g["volume"]).max() <= TOL
+    m = legacy_mesh.create_mesh(wrapped, sample.latent.to(dev), str(tmp_path / "legacy"), N=N)
+    rv, rf = mo.read_ply(str(tmp_path / "legacy.ply"))
+    assert rf.shape[0] == m.faces.shape[0] > 0
+    v, f, _ = mo.marching_cubes(sdf[:, 0].cpu().numpy().reshape(N, N, N), 0.0, [2.0 / (N - 1)] * 3)
+    assert np.array_equal(rf, f)
+    assert np.array_equal(rv, (np.float32(-1) + v).astype(np.float32))
+
+
+def test_full_size_properties_128(dev):
+    """BASELINE config #2 size (128^3 hand+obj): properties that need no CPU oracle run."""
+    dec = synthetic.make_decoder(0)
+    s = helpers.to_cuda(synthetic.make_sample(0))
+    N = 128
+    v1 = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N)
+    v2 = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N)
+    assert torch.equal(v1["hand"], v2["hand"]) and torch.equal(v1["obj"], v2["obj"])      # deterministic
+    # sampled oracle check on 4096 random grid indices of pass 2
+    idx = torch.randint(0, N ** 3, (4096,), generator=torch.Generator().manual_seed(0))
+    xyz = orc.grid_points(N, v1["voxel"], v1["origin"])[idx]
+    sc = s.to(torch.device("cpu"))
+    with torch.no_grad():
+        h, o, _ = orc.decode_points(dec.state_dict(), orc.decoder_cfg(dec), sc.latent, xyz, sc.specs,
+                                    sc.mano_results, sc.obj_results)
+    assert (v1["hand"].view(-1)[idx.to(dev)].cpu() - h[:, 0]).abs().max() <= TOL
+    assert (v1["obj"].view(-1)[idx.to(dev)].cpu() - o[:, 0]).abs().max() <= TOL
+    for tag in ("hand", "obj"):
+        out = engine.marching_cubes(v1[tag], 0.0, [float(v1["voxel"])] * 3)
+        inv = mo.mesh_invariants(out["verts"].cpu().numpy(), out["faces"].cpu().numpy())
+        assert inv["nonmanifold_edges"] == 0 and inv["oriented"] and inv["closed"], (tag, inv)
+        # every vertex lies within half a voxel of the iso-surface of the trilinear field
+        assert out["faces"].shape[0] > 1000
