@@ -76,6 +76,8 @@ class BoundSample:
         if bbox:
             box = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3,
                                dtype=torch.int32, device=dev)
+        if n == 0:                      # empty query: nothing to launch
+            return hand, obj, cls, box
         L = _lib.lib()
         use_tc = self.tc is not None and not want_cls and path in ("auto", "tc")
         if path == "tc" and not use_tc:
@@ -186,11 +188,12 @@ def _decode_ordered(bits: int) -> float:
 
 
 def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
-                   index0_offset=0, want_keys=False):
+                   index0_offset=0, want_keys=False, check_range=True):
     """GPU marching cubes.  vol: CUDA f32 [n0,n1,n2].  Returns dict of CUDA tensors
     verts [V,3] (array-axis order x spacing), points [V,3] (= origin + verts), faces [F,3] int32,
     keys [V] int64 (when want_keys).  Raises ValueError like skimage when level is outside the
-    data range (the reference catches it, utils/mesh.py:353-358)."""
+    data range (the reference catches it, utils/mesh.py:353-358); ``check_range=False`` (z-slabs,
+    where an empty slab is normal) returns empty tensors instead."""
     _lib.require_cuda(vol, "vol")
     vol = vol.to(torch.float32).contiguous()
     if vol.dim() != 3:

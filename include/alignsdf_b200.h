@@ -85,6 +85,10 @@ typedef struct {
 int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* sample_dev,
                  const asdf_query* q, float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev,
                  void* stream);
+/* Layout self test of the tensor-core path: D[128,256] = A[128,64] . B[256,64]^T through the same
+ * operand layouts / descriptors / TMEM read-back as asdf_tc_eval (a_rows_dev fp16 row-major,
+ * b_tiles_dev two pre-swizzled 16 KiB tiles, d_out_dev f32). */
+int asdf_tc_selftest(const void* a_rows_dev, const void* b_tiles_dev, float* d_out_dev, void* stream);
 /* Bytes of the packed static stream / floats of the per-sample block the tcgen05 path expects. */
 int64_t asdf_tc_static_bytes(void);
 int64_t asdf_tc_sample_floats(void);

@@ -1,0 +1,69 @@
+"""Tensor-core (tcgen05) path on the GPU: operand-layout self test, then parity vs reference golden."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from alignsdf_b200 import _lib, engine, mesh as amesh, packer, tc_pack
+from oracle import alignsdf_oracle as orc
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def test_umma_layout_selftest():
+    """D = A.B^T (M=128 over a CTA pair, N=256, K=64) through the production operand layouts."""
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((128, 64)).astype(np.float16)
+    b = rng.standard_normal((256, 64)).astype(np.float16)
+    tiles = np.stack([tc_pack.swizzle_tile(b[:128]), tc_pack.swizzle_tile(b[128:])])
+    dev = torch.device("cuda")
+    a_d = torch.from_numpy(a).to(dev)
+    b_d = torch.from_numpy(tiles).to(dev)
+    d_d = torch.full((128, 256), float("nan"), dtype=torch.float32, device=dev)
+    rc = _lib.lib().asdf_tc_selftest(_lib.ptr(a_d), _lib.ptr(b_d), _lib.ptr(d_d), _lib.stream_ptr(dev))
+    _lib.check(rc, "asdf_tc_selftest")
+    torch.cuda.synchronize()
+    want = a.astype(np.float64) @ b.astype(np.float64).T
+    got = d_d.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() < 1e-3, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("name", ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_hand6_n12",
+                                  "sep_obj6_n12", "sep_both54_n12", "sep_both9_n32_handonly",
+                                  "sep_both9_n20_objonly"])
+def test_tc_two_pass_fields_match_reference_golden(name):
+    meta, g, dec, sample = helpers.load_case(name)
+    s = helpers.to_cuda(sample)
+    hb, ob = meta.get("hand_branch", True), meta.get("obj_branch", True)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob, path="tc")
+    assert np.float32(float(vols["voxel"])) == g["new_voxel"]
+    assert np.array_equal(vols["origin"].numpy(), g["new_origin"])
+    for key, vol in (("pass1_hand", vols["pass1_hand"]), ("pass1_obj", vols["pass1_obj"]),
+                     ("pass2_hand", vols["hand"]), ("pass2_obj", vols["obj"])):
+        if key in g:
+            err = np.abs(vol.cpu().numpy() - g[key]).max()
+            assert err <= TOL, (key, err)
+
+
+def test_tc_matches_generic_fp32_kernel_and_is_deterministic():
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    bound = engine.get_engine(dec, torch.device("cuda")).bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    N = 40                                    # 64000 points: 500 tiles, > 3 waves of 74 CTA pairs
+    ht, ot, _, bt = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="tc")
+    hs, os_, _, bs = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="simt")
+    assert (ht - hs).abs().max() <= 2e-6 and (ot - os_).abs().max() <= 2e-6
+    ht2, ot2, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="tc")
+    assert torch.equal(ht, ht2) and torch.equal(ot, ot2)
+    # ragged ranges: not a multiple of the 128-point tile, odd begin
+    h3, o3, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], begin=77, end=77 + 1001, path="tc")
+    assert torch.equal(h3, ht[77:77 + 1001]) and torch.equal(o3, ot[77:77 + 1001])
+    # explicit points
+    xyz = (torch.rand(777, 3, generator=torch.Generator().manual_seed(2)) * 2 - 1).cuda()
+    hp, op, _ = bound.eval_points(xyz, path="tc")
+    hq, oq, _ = bound.eval_points(xyz, path="simt")
+    assert (hp - hq).abs().max() <= 2e-6 and (op - oq).abs().max() <= 2e-6
