@@ -17,6 +17,7 @@ from . import _lib, packer
 from ._lib import AsdfError
 
 INT_MAX = 2 ** 31 - 1
+LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
 
@@ -89,12 +90,14 @@ class BoundSample:
                                     _lib.ptr(self.tc.sample), C.byref(q), _lib.ptr(hand),
                                     _lib.ptr(obj), _lib.ptr(box), st)
                 _lib.check(rc, "asdf_tc_eval")
+                LAUNCHES["count"] += 1
             else:
                 rc = L.asdf_simt_eval(C.byref(self.simt_desc), _lib.ptr(self.engine.simt_static),
                                       _lib.ptr(self.simt_sample), _lib.ptr(self.engine.cls_dev),
                                       C.byref(q), _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(cls),
                                       _lib.ptr(box), st)
                 _lib.check(rc, "asdf_simt_eval")
+                LAUNCHES["count"] += 1
         return hand, obj, cls, box
 
     def eval_grid(self, N, voxel, origin, mode="reference", begin=0, end=None, bbox_mask=0,
@@ -214,6 +217,7 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
         totals = torch.empty(4, dtype=torch.int64, device=dev)
         _lib.check(L.asdf_mc_count(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(totals), st),
                    "asdf_mc_count")
+        LAUNCHES["count"] += 5
         nv, nt, mn, mx = (int(x) for x in totals.cpu())
         if not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
             raise ValueError("Surface level must be within volume data range.")
@@ -225,6 +229,7 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
             _lib.check(L.asdf_mc_emit(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(verts),
                                       _lib.ptr(points), _lib.ptr(faces), _lib.ptr(keys), st),
                        "asdf_mc_emit")
+            LAUNCHES["count"] += 1
     return dict(verts=verts, points=points, faces=faces, keys=keys)
 
 

@@ -1,0 +1,198 @@
+"""z-slab sharding of one reconstruction across the GPUs of a box.
+
+The reference only has sample-level parallelism (dist_reconstruct.py:63-84: one subprocess per
+GPU, no communication).  This module adds the north star's second mode: grid axis 0 is cut into
+``world`` contiguous slabs, one process per GPU (torchrun / torch.distributed):
+
+  pass 1   each rank evaluates its slab and reduces a local bbox   -> ONE all_reduce(MIN) of 12 ints
+  re-grid  identical arithmetic on every rank                       (utils/mesh.py:249-254)
+  pass 2   each rank evaluates its slab of the refit grid
+  halo     every rank publishes its first plane (both fields)       -> ONE all_gather of [2,N,N] f32
+  MC       each rank meshes [z0, z1] (its slab + the neighbour's first plane) with global keys
+  gather   vertex / face / key lists go to rank 0                   -> all_gather of counts + padded data
+  stitch   rank 0 merges duplicate boundary vertices by key; the result is bit-identical to the
+           single-GPU mesh (same vertex order = key order, same face order = cell order).
+
+The numerical kernels are injected (``Backend``) so the collective / stitching logic can be tested
+on CPU with gloo (tests/test_slab_gloo.py uses the oracle as backend); ``GpuBackend`` is the
+product backend.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+INT_MAX = 2 ** 31 - 1
+
+
+def slab_planes(N: int, rank: int, world: int):
+    """Planes [z0, z1) of axis 0 owned by ``rank`` (as even as possible, contiguous)."""
+    base, rem = divmod(N, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class Backend:
+    """eval(begin, end, voxel, origin, bbox_mask) -> (hand [n], obj [n], box int32[12] | None);
+    mc(vol [m,N,N], voxel, origin, index0_offset) -> (verts [V,3] f32, points [V,3] f32, faces [F,3] i32, keys [V] i64)"""
+    eval: callable
+    mc: callable
+    device: torch.device
+
+
+def reduce_bbox(box: torch.Tensor, group=None) -> torch.Tensor:
+    """Global bbox from per-rank {min x3, max x3} x2 with a single MIN all-reduce (max is negated)."""
+    b = box.clone().to(torch.int32)
+    sign = torch.tensor([1, 1, 1, -1, -1, -1] * 2, dtype=torch.int32, device=b.device)
+    b = b * sign
+    dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
+    return b * sign
+
+
+def exchange_halo(first_planes: torch.Tensor, rank: int, world: int, group=None):
+    """all_gather of every rank's first plane; returns the next rank's plane (None on the last)."""
+    buf = [torch.empty_like(first_planes) for _ in range(world)]
+    dist.all_gather(buf, first_planes.contiguous(), group=group)
+    return buf[rank + 1] if rank + 1 < world else None
+
+
+def gather_varlen(t: torch.Tensor, world: int, group=None):
+    """all_gather of tensors whose first dimension differs per rank (pad to the max)."""
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x) for x in ns]
+    m = max(ns + [1])
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return [o[:k] for o, k in zip(out, ns)]
+
+
+def stitch(parts):
+    """parts: per rank (verts, points, faces, keys) numpy.  Merge duplicate boundary vertices by
+    key; vertex order = key order, face order = rank (== cell) order."""
+    keys = np.concatenate([p[3] for p in parts])
+    if keys.size == 0:
+        return (np.zeros((0, 3), np.float32),) * 2 + (np.zeros((0, 3), np.int32),)
+    verts = np.concatenate([p[0] for p in parts])
+    points = np.concatenate([p[1] for p in parts])
+    uk, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    faces, off = [], 0
+    for p in parts:
+        faces.append(inv[p[2].astype(np.int64) + off])
+        off += p[3].shape[0]
+    return verts[first], points[first], np.concatenate(faces).astype(np.int32)
+
+
+def two_pass_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=True, obj_branch=True,
+                  group=None):
+    """Both evaluation passes on this rank's slab.  Returns dict(hand, obj [nz,N,N], voxel, origin,
+    z0, z1) -- ``voxel``/``origin`` identical on every rank."""
+    from .mesh import _bbox_to_minmax, _regrid
+    z0, z1 = slab_planes(N, rank, world)
+    mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
+    vs1 = 2.0 / (N - 1)
+    _, _, box = backend.eval(z0 * N * N, z1 * N * N, vs1, [-1.0, -1.0, -1.0], mask)
+    if box is None:                                   # empty slab (more ranks than planes)
+        box = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3, dtype=torch.int32,
+                           device=backend.device)
+    box = reduce_bbox(box, group)
+    mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
+    voxel, origin = _regrid(mn, mx, N, vs1)
+    h, o, _ = backend.eval(z0 * N * N, z1 * N * N, float(voxel), origin.tolist(), 0)
+    return dict(hand=h.view(z1 - z0, N, N), obj=o.view(z1 - z0, N, N), voxel=voxel, origin=origin, z0=z0, z1=z1)
+
+
+def mesh_slab(backend: Backend, fields: dict, N: int, rank: int, world: int, which=("hand", "obj"), group=None):
+    """Halo exchange + marching cubes + gather + stitch.  Returns {tag: (verts, points, faces)} on
+    rank 0 (numpy) and None elsewhere."""
+    z0, z1 = fields["z0"], fields["z1"]
+    nz = z1 - z0
+    first = torch.stack([fields["hand"][0] if nz else torch.zeros(N, N, device=backend.device),
+                         fields["obj"][0] if nz else torch.zeros(N, N, device=backend.device)])
+    halo = exchange_halo(first, rank, world, group)
+    vs = float(fields["voxel"])
+    org = fields["origin"].tolist()
+    out = {}
+    for ti, tag in enumerate(("hand", "obj")):
+        if tag not in which:
+            continue
+        vol = fields[tag]
+        if halo is not None and nz:
+            vol = torch.cat([vol, halo[ti:ti + 1]], 0)
+        if vol.shape[0] >= 2:
+            v, p, f, k = backend.mc(vol.contiguous(), vs, org, z0)
+        else:
+            dev = backend.device
+            v = p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
+            f = torch.zeros((0, 3), dtype=torch.int32, device=dev)
+            k = torch.zeros((0,), dtype=torch.int64, device=dev)
+        gv, gp = gather_varlen(v, world, group), gather_varlen(p, world, group)
+        gf, gk = gather_varlen(f, world, group), gather_varlen(k, world, group)
+        if rank == 0:
+            parts = [(a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy(), d.cpu().numpy())
+                     for a, b, c, d in zip(gv, gp, gf, gk)]
+            out[tag] = stitch(parts)
+    return out if rank == 0 else None
+
+
+# ----------------------------------------------------------------------------
+# product backend + public entry point
+# ----------------------------------------------------------------------------
+def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
+    from . import engine
+
+    def ev(begin, end, voxel, origin, bbox_mask):
+        if end <= begin:
+            e = torch.zeros(0, dtype=torch.float32, device=bound.device)
+            return e, e.clone(), None
+        h, o, _, box = bound.eval_grid(N, voxel, origin, grid_mode, begin, end, bbox_mask, path=path)
+        return h, o, box
+
+    def mc(vol, voxel, origin, index0_offset):
+        r = engine.marching_cubes(vol, 0.0, [voxel] * 3, origin, index0_offset, want_keys=True,
+                                  check_range=False)
+        return r["verts"], r["points"], r["faces"], r["keys"]
+
+    return Backend(ev, mc, bound.device)
+
+
+def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,
+                                      obj_results, cam_intr, specs, filename, N=256, group=None,
+                                      grid_mode="reference", write=True):
+    """z-slab sharded equivalent of ``mesh.create_mesh_combined_decoder`` (call on every rank of an
+    initialised process group; rank 0 writes the files and returns the meshes)."""
+    import logging
+    from . import engine
+    from .mesh import Mesh, _split
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = engine._device_of(latent_vec)
+    bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
+    be = gpu_backend(bound, N, grid_mode)
+    fields = two_pass_slab(be, N, rank, world, hand_branch, obj_branch, group)
+    which = tuple(t for t, use in (("hand", hand_branch), ("obj", obj_branch)) if use)
+    meshes = mesh_slab(be, fields, N, rank, world, which, group)
+    if rank != 0:
+        return None
+    result = {"hand": None, "obj": None}
+    for tag in which:
+        verts, points, faces = meshes[tag]
+        if faces.shape[0] == 0:
+            logging.warning("Cannot reconstruct mesh from '{}'".format(f"{filename}_{tag}.ply"))
+            continue
+        if tag == "obj" and hand_branch:
+            points = points * np.array([1]) + np.array([0, 0, 0])      # utils/mesh.py:366-369, hand's values
+        m = Mesh(points, faces)
+        pieces = _split(m)
+        if len(pieces) > 1:
+            m = max(pieces, key=lambda x: x.area)
+        if write:
+            m.export(f"{filename}_{tag}.ply")
+        result[tag] = m
+    return result

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- dense-grid SDF query + marching cubes at 256^3 hand+object (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--N 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = the whole hot path for one synthetic sample (utils/mesh.py::create_mesh_combined_decoder
+semantics): pass 1 over the N^3 grid, bbox re-grid, pass 2, marching cubes of the hand and of the
+object field.  One step therefore answers 2*N^3 hand+object SDF queries.
+
+  value   M hand+obj queries/s, inputs (latent, pose, weights) already resident in HBM, timed with
+          CUDA events on the launching stream, max over ranks.
+  e2e     the same work through the public API (create_mesh_combined_decoder[_slab]) with the
+          per-step inputs coming from pinned host memory and the meshes read back to the host and
+          written as PLY -- H2D/D2H inside the timed region.
+  N > 1   z-slab sharding of every sample across the ranks (strong scaling): one all_reduce of the
+          bbox, one all_gather of the boundary planes, gather of the mesh pieces to rank 0.
+  --impl reference   the reference's own torch-CPU path (oracle port: /root/reference cannot travel
+          to the GPU box) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_MIN = 2_086_912          # algorithmic FLOP per hand+obj query after folding
+F_REF = 3_147_776          # FLOP per query as the reference executes it
+N_SAMPLES = 16             # BASELINE config #3: batch of 16 synthetic latents / poses
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), tflops_burst=float(p["bf16_tflops"]),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, power_w_max=max(pw) if pw else None, samples=len(self.rows))
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's torch-CPU path (oracle port)
+# ----------------------------------------------------------------------------
+def cpu_reference_rate(N, chunks, warm=1):
+    """M hand+obj queries/s of the reference's per-chunk work (grid -> embedding -> cat -> decoder,
+    chunk = 2**18 points as in reconstruct.py:93) on all host cores."""
+    from alignsdf_b200 import synthetic
+    from oracle import alignsdf_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    dec = synthetic.make_decoder(0)
+    s = synthetic.make_sample(0)
+    sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    cfg = orc.decoder_cfg(dec)
+    P = 2 ** 18
+    times = []
+    with torch.no_grad():
+        for c in range(warm + chunks):
+            start = (c * P) % max(N ** 3 - P, 1)
+            t0 = time.perf_counter()
+            orc.eval_volume(sd, cfg, s.latent, s.specs, s.mano_results, s.obj_results, N, 2.0 / (N - 1),
+                            [-1, -1, -1], "reference", P, start, start + P)
+            if c >= warm:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return P / sec / 1e6, sec, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    rate, sec, cores = cpu_reference_rate(args.N, max(args.steps, 1), max(args.warmup, 1))
+    line = dict(
+        metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=rate, unit="Mq/s",
+        impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+        data="synthetic",
+        config=dict(workload=f"{args.N}^3 hand+obj, 2 passes + 2 marching cubes, {N_SAMPLES} synthetic latents/poses",
+                    decoder="SeparateDecoder 5x512, both/9", chunk=2 ** 18),
+        cpu_baseline=dict(value=rate, unit="Mq/s", cores=cores, kind="port",
+                          sample=f"{args.steps} chunks of 2^18 grid points of the {args.N}^3 workload through "
+                                 "the oracle port of the reference's torch-CPU path (marching cubes excluded: "
+                                 "scikit-image is not installable)"),
+        e2e=dict(value=rate, unit="Mq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        wall_s=time.perf_counter() - t_all)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--N", type=int, default=256)
+    ap.add_argument("--cpu-chunks", type=int, default=6, help="chunks of 2^18 points for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from alignsdf_b200 import engine, mesh as amesh, slab, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.N
+    W, K = max(args.warmup, 3), args.steps
+
+    dec = synthetic.make_decoder(0)
+    host_samples = []
+    for i in range(N_SAMPLES):                 # per-step inputs live in PINNED host memory
+        s = synthetic.make_sample(i)
+        pin = lambda t: t.contiguous().pin_memory()
+        host_samples.append(synthetic.Sample(pin(s.latent), {k: pin(v) for k, v in s.mano_results.items()},
+                                             {k: pin(v) for k, v in s.obj_results.items()}, s.specs))
+    h2d_bytes = sum(t.numel() * 4 for t in [host_samples[0].latent, *host_samples[0].mano_results.values(),
+                                            *host_samples[0].obj_results.values()])
+    eng = engine.get_engine(dec, dev)          # weights packed + resident in HBM once
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    kernel_ms = []
+
+    def step_device(i, bound):
+        """Device-resident step: 2 passes + 2 marching cubes (+ slab collectives when world > 1)."""
+        if world == 1:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mask = 3
+            ev0.record()
+            h1, o1, _, box = bound.eval_grid(N, 2.0 / (N - 1), [-1.0, -1.0, -1.0], bbox_mask=mask)
+            ev1.record()
+            mn, mx = amesh._bbox_to_minmax(box, True, True)
+            voxel, origin = amesh._regrid(mn, mx, N, 2.0 / (N - 1))
+            h2, o2, _, _ = bound.eval_grid(N, float(voxel), origin.tolist())
+            vs = float(voxel)
+            for vol in (h2, o2):
+                engine.marching_cubes(vol.view(N, N, N), 0.0, [vs] * 3, origin.tolist(), check_range=False)
+            kernel_ms.append((ev0, ev1))
+        else:
+            be = slab.gpu_backend(bound, N)
+            fields = slab.two_pass_slab(be, N, rank, world)
+            slab.mesh_slab(be, fields, N, rank, world)
+
+    def bind(i):
+        s = host_samples[i % N_SAMPLES].to(dev)
+        return eng.bind(s.latent, s.specs, s.mano_results, s.obj_results)
+
+    # ---------------- device-resident timing ----------------
+    bounds = [bind(i) for i in range(N_SAMPLES)]
+    for i in range(W):
+        step_device(i, bounds[i % N_SAMPLES])
+    kernel_ms.clear()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = engine.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step_device(i, bounds[i % N_SAMPLES])
+    e1.record()
+    barrier()
+    launches = engine.LAUNCHES["count"] - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    k1_ms = [a.elapsed_time(b) for a, b in kernel_ms]
+
+    # ---------------- end-to-end through the public API ----------------
+    tmp = tempfile.mkdtemp(prefix="asdf_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    d2h_bytes = [0]
+
+    def step_e2e(i):
+        s = host_samples[i % N_SAMPLES].to(dev)          # H2D of this step's inputs (pinned -> device)
+        prefix = os.path.join(tmp, f"s{rank}_{i % 2}")
+        if world == 1:
+            res = amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results,
+                                                     s.obj_results, None, s.specs, prefix, N=N)
+        else:
+            res = slab.create_mesh_combined_decoder_slab(True, True, False, dec, s.latent, s.mano_results,
+                                                         s.obj_results, None, s.specs, prefix, N=N)
+        if res is not None:
+            d2h_bytes[0] = sum(m.vertices.nbytes + m.faces.nbytes for m in res.values() if m is not None)
+
+    for i in range(W):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---------------- max over ranks ----------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    queries = 2.0 * N ** 3 * K
+    value = queries / (ms * 1e-3) / 1e6
+    e2e_value = queries / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks = measured_peaks()
+        line = dict(
+            metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=value, unit="Mq/s",
+            n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
+            scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f16x3 (fp32 accumulate)",
+            data="synthetic", impl="b200",
+            config=dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {N_SAMPLES} synthetic latents/poses",
+                        decoder="SeparateDecoder 5x512, both/9", parallelism=f"zslab{world}" if world > 1 else "single",
+                        l2="outputs (2 x 67 MB per pass) exceed L2; the 4 MB weight stream is L2-resident by design",
+                        meshes_per_s=K / (ms * 1e-3), decoder_evals_Mps=2 * value),
+            e2e=dict(value=e2e_value, unit="Mq/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes[0],
+                     ms_per_step=e2e_ms / K, meshes_per_s=K / (e2e_ms * 1e-3)),
+            gpu_launches=launches, clocks=clocks)
+        if world == 1 and k1_ms:
+            k1 = sum(k1_ms) / len(k1_ms)
+            ach = N ** 3 * F_MIN / (k1 * 1e-3) / 1e12
+            line["roofline"] = dict(bound="tensor", kernel="tc_eval_kernel", achieved=ach, peak=peaks["tflops"],
+                                    unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+                                    ms_per_launch=k1, queries_per_launch=N ** 3, flop_per_query=F_MIN,
+                                    issued_tflops=ach * 3 * (2 * 2 * 524288) / F_MIN,
+                                    frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
+                                    Mq_per_s_kernel=N ** 3 / (k1 * 1e-3) / 1e6)
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores = cpu_reference_rate(N, args.cpu_chunks)
+            line["cpu_baseline"] = dict(value=rate, unit="Mq/s", cores=cores, kind="port",
+                                        sample=f"{args.cpu_chunks} chunks of 2^18 grid points of the same {N}^3 workload "
+                                               f"({sec:.2f} s/chunk) through the oracle port of the reference's torch-CPU path")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

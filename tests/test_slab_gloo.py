@@ -1,0 +1,104 @@
+"""world_size-2 gloo test (CPU) of the z-slab sharding logic: bbox all-reduce, halo all-gather,
+variable-length gather and key-based stitching.  The numerical kernels are replaced by the oracle
+(the product backend needs a GPU); the result must equal the single-process oracle bit for bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from alignsdf_b200 import slab
+from oracle import alignsdf_oracle as orc
+from oracle import mc_oracle as mo
+from tests import helpers
+
+
+def _oracle_backend(dec, sample, N):
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    cfg = orc.decoder_cfg(dec)
+
+    def ev(begin, end, voxel, origin, mask):
+        if end <= begin:
+            e = torch.zeros(0)
+            return e, e.clone(), None
+        with torch.no_grad():
+            h, o, _ = orc.eval_volume(sd, cfg, sample.latent, sample.specs, sample.mano_results,
+                                      sample.obj_results, N, voxel, origin, "reference", 2 ** 18, begin, end)
+        box = None
+        if mask:
+            box = torch.tensor([slab.INT_MAX] * 3 + [-1] * 3 + [slab.INT_MAX] * 3 + [-1] * 3, dtype=torch.int32)
+            for bi, vals in enumerate((h, o)):
+                if not (mask >> bi) & 1:
+                    continue
+                idx = torch.nonzero(vals < 0)[:, 0] + begin
+                if idx.numel():
+                    ijk = torch.stack([idx // (N * N), (idx // N) % N, idx % N], 1)
+                    box[6 * bi:6 * bi + 3] = ijk.min(0).values.int()
+                    box[6 * bi + 3:6 * bi + 6] = ijk.max(0).values.int()
+        return h, o, box
+
+    def mc(vol, voxel, origin, z0):
+        try:
+            v, f, k = mo.marching_cubes(vol.numpy(), 0.0, [voxel] * 3, (z0, 0, 0), (N, N, N))
+        except ValueError:
+            v, f, k = np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32), np.zeros(0, np.uint64)
+        p = (np.asarray(origin, np.float32)[None] + v).astype(np.float32)
+        return (torch.from_numpy(v), torch.from_numpy(p), torch.from_numpy(f),
+                torch.from_numpy(k.astype(np.int64)))
+
+    return slab.Backend(ev, mc, torch.device("cpu"))
+
+
+def _worker(rank, world, port, name, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        meta, g, dec, sample = helpers.load_case(name)
+        N = meta["N"]
+        be = _oracle_backend(dec, sample, N)
+        fields = slab.two_pass_slab(be, N, rank, world)
+        meshes = slab.mesh_slab(be, fields, N, rank, world)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=float(fields["voxel"]),
+                 origin=fields["origin"].numpy(), hand=fields["hand"].numpy(), z0=fields["z0"], z1=fields["z1"])
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "mesh.npz"),
+                     **{f"{t}_{n}": a for t in meshes for n, a in zip(("v", "p", "f"), meshes[t])})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_planes_partition():
+    for N, w in ((256, 8), (24, 2), (10, 4), (3, 8)):
+        cuts = [slab.slab_planes(N, r, w) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == N
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_rank_slab_reconstruction_equals_single_process(tmp_path, world):
+    name = "sep_both9_n24"
+    port = 29500 + os.getpid() % 2000 + world
+    mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
+    meta, g, dec, sample = helpers.load_case(name)
+    N = meta["N"]
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    # identical re-grid on every rank, equal to the reference's golden values
+    for p in parts:
+        assert np.float32(p["voxel"]) == g["new_voxel"] and np.array_equal(p["origin"], g["new_origin"])
+    hand = np.concatenate([p["hand"] for p in parts], 0)
+    assert np.abs(hand - g["pass2_hand"]).max() <= 1e-6
+    m = np.load(tmp_path / "mesh.npz")
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs, sample.mano_results,
+                                 sample.obj_results, N)
+    for tag in ("hand", "obj"):
+        v, f, _ = mo.marching_cubes(res[tag].numpy(), 0.0, [float(res["voxel"])] * 3)
+        assert np.array_equal(m[f"{tag}_f"], f)
+        assert np.array_equal(m[f"{tag}_v"], v)
+        assert np.array_equal(m[f"{tag}_p"], (res["origin"].numpy()[None] + v).astype(np.float32))
