@@ -37,7 +37,7 @@ class SimtDesc(C.Structure):
 
 class TcDesc(C.Structure):
     _fields_ = [("h", C.c_int32 * 2), ("act_scale", C.c_float), ("w_scale", (C.c_float * 3) * 2),
-                ("branch_stride", C.c_int64)]
+                ("branch_stride", C.c_int64), ("debug_dev", C.c_void_p)]
 
 
 class McParams(C.Structure):

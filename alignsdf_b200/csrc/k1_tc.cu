@@ -44,7 +44,7 @@ constexpr int kChunkK = 64;                // K elements per swizzle atom row (1
 constexpr int kTileBytes = 128 * kChunkK * 2;       // one B tile: 128 rows x 64 k  = 16 KiB
 constexpr int kASlotBytes = kPtsPerCta * kChunkK * 2;  // one A chunk: 64 rows x 64 k =  8 KiB
 constexpr int kNumASlots = 8;
-constexpr int kRing = 4;                   // B tiles in flight
+constexpr int kRing = 5;                   // B tiles in flight
 constexpr int kTilesPerDecoder = 64;       // 16 (L1) + 16 (L2) + 32 (L3)
 constexpr int kStaticParamFloats = 256 + 1024 + 8;   // b1*t | (b3, w4) pairs | b4, 1/s1, 1/s2, 1/(s3 t)
 constexpr int64_t kWeightBytes = (int64_t)2 * 2 * kTilesPerDecoder * kTileBytes;   // [dec][cta][tile]
@@ -54,13 +54,13 @@ constexpr int kSampleFloatsPerDecoder = 2 * 512 * 4;   // M0B0[512][4] | M2B2[51
 constexpr int kOffAHi = 0;
 constexpr int kOffALo = kOffAHi + kNumASlots * kASlotBytes;          //  65536
 constexpr int kOffRing = kOffALo + kNumASlots * kASlotBytes;         // 131072
-constexpr int kOffM0 = kOffRing + kRing * kTileBytes;                // 196608
-constexpr int kOffM2 = kOffM0 + 512 * 16;
+constexpr int kOffM2 = kOffRing + kRing * kTileBytes;                // 212992
 constexpr int kOffB1 = kOffM2 + 512 * 16;
 constexpr int kOffB3W4 = kOffB1 + 256 * 4;
 constexpr int kOffRed = kOffB3W4 + 512 * 8;                          // [4][64] partial sums
 constexpr int kOffMisc = kOffRed + 4 * 64 * 4;                       // 8 floats of scalars
-constexpr int kOffBar = kOffMisc + 64;
+constexpr int kOffPts = kOffMisc + 64;                               // [64] float4 points of this CTA's rows
+constexpr int kOffBar = kOffPts + 64 * 16;
 // barriers (8 B each)
 constexpr int kBarFull = 0;                       // [kRing]   leader: own tx + peer relay arrive
 constexpr int kBarFullLocal = kBarFull + kRing;   // [kRing]   peer CTA: own tx only
@@ -103,12 +103,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Plain (CTA-scope release)
+// arrive as in CUTLASS' ClusterBarrier::arrive: the payload it orders lives in this CTA's shared
+// memory and has already been made visible to the async proxy (fence.proxy.async / TMA
+// complete_tx); `.release.cluster` would compile to MEMBAR.ALL.GPU on every call.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       :: "r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -151,12 +154,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// explicit shared-state-space accesses (32-bit shared addresses): keeps ptxas on LDS/STS
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t a) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // operand write-back: 8 consecutive k of one row, split into fp16 hi + lo, 128B-swizzled K-major
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split8_store(uint8_t* a_hi_slot, uint8_t* a_lo_slot, int row, int k8, const float* v) {
+__device__ __forceinline__ void split8_store(uint32_t a_hi_slot, uint32_t a_lo_slot, int row, int k8, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -168,8 +195,8 @@ __device__ __forceinline__ void split8_store(uint8_t* a_hi_slot, uint8_t* a_lo_s
     lo[i] = *reinterpret_cast<const uint32_t*>(&l);
   }
   const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((k8 ^ (row & 7)) << 4);
-  *reinterpret_cast<uint4*>(a_hi_slot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(a_lo_slot + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  sts_u4(a_hi_slot + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  sts_u4(a_lo_slot + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
 
 struct Args {
@@ -180,15 +207,16 @@ struct Args {
   float* out_hand;
   float* out_obj;
   int32_t* bbox;
+  long long* dbg;          // optional phase timing (cluster 0): see asdf_tc_desc.debug_dev
 };
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval_kernel(const Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];    // 128B-swizzle atoms need 1024 B alignment
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -201,7 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       mbar_init(bar(kBarFullLocal + i), 1);
       mbar_init(bar(kBarEmpty + i), 1);
     }
-    for (int i = 0; i < kNumASlots; ++i) mbar_init(bar(kBarAFull + i), 4);   // 2 warps x 2 CTAs
+    for (int i = 0; i < kNumASlots; ++i) mbar_init(bar(kBarAFull + i), 16);  // see publish()
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarTmemFull + i), 1);
     fence_mbar_init();
   }
@@ -223,12 +251,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
     // =========================== weight-stream producer ===========================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      const bool dbg_nocopy = a.dbg != nullptr && (a.dbg[15] & 1);   // timing experiment: skip the copies
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
         for (int dec = 0; dec < 2; ++dec) {
           const uint8_t* src = a.stat + ((int64_t)(dec * 2 + rank) * kTilesPerDecoder) * kTileBytes;
           for (int i = 0; i < kTilesPerDecoder; ++i) {
             mbar_wait(bar(kBarEmpty + slot), phase ^ 1);
             const uint32_t fb = bar((leader ? kBarFull : kBarFullLocal) + slot);
+            if (dbg_nocopy) {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(fb) : "memory");
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx(fb, kTileBytes);
             bulk_g2s(sbase + kOffRing + slot * kTileBytes, src + (int64_t)i * kTileBytes, kTileBytes, fb);
             if (++slot == kRing) { slot = 0; phase ^= 1; }
@@ -253,10 +287,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         // =================================== UMMA issuer ===================================
         uint32_t slot = 0, phase = 0, a_phase = 0 /* bit per A slot */;
         const uint32_t a_hi = sbase + kOffAHi, a_lo = sbase + kOffALo, ring = sbase + kOffRing;
+        long long w_a = 0, w_b = 0, t_begin = clock64();
         // one K chunk (64) of one N block: hi tile then lo tile of the ring
         auto chunk = [&](int a_slot, uint32_t d_tmem, bool first) {
           const uint32_t ah = a_hi + a_slot * kASlotBytes, al = a_lo + a_slot * kASlotBytes;
+          long long t0 = clock64();
           mbar_wait(bar(kBarFull + slot), phase);
+          w_b += clock64() - t0;
           tc_fence_after();
           uint32_t b = ring + slot * kTileBytes;
 #pragma unroll
@@ -267,7 +304,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
             umma_f16_cg2(d_tmem, smem_desc(al + ks * 32), smem_desc(b + ks * 32), kIdesc, 1u);
           umma_commit_both(bar(kBarEmpty + slot));
           if (++slot == kRing) { slot = 0; phase ^= 1; }
+          t0 = clock64();
           mbar_wait(bar(kBarFull + slot), phase);
+          w_b += clock64() - t0;
           tc_fence_after();
           b = ring + slot * kTileBytes;
 #pragma unroll
@@ -277,7 +316,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
           if (++slot == kRing) { slot = 0; phase ^= 1; }
         };
         auto wait_a = [&](int a_slot) {
+          const long long t0 = clock64();
           mbar_wait(bar(kBarAFull + a_slot), (a_phase >> a_slot) & 1u);
+          w_a += clock64() - t0;
           a_phase ^= 1u << a_slot;
           tc_fence_after();
         };
@@ -302,6 +343,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
             }
           }
         }
+        if (a.dbg && cluster_id == 0) {
+          a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_a; a.dbg[2] = w_b;
+        }
       }
     }
     __syncwarp();
@@ -309,20 +353,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
     // =================================== epilogue warps ===================================
     const int e = warp - kEpiWarp0;            // 0..7
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int ch = e >> 2;                     // which 64-column half of the 128-column buffer
-    const int row = (q & 1) * 32 + lane;       // point row inside this CTA (0..63)
+    const int ch = e >> 2;                     // 0: 32-column groups {0,2}; 1: groups {1,3} of a buffer
+    const int row = (q & 1) * 32 + lane;       // point row of this thread's TMEM lane (0..63)
     const int nhalf = q >> 1;                  // accumulator n-half held by this lane quadrant
-    const int cbase = nhalf * 2 + ch;          // 64-wide feature chunk (0..3) inside a 256-wide N block
     const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..255
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float4* sM0 = reinterpret_cast<float4*>(smem + kOffM0);
-    float4* sM2 = reinterpret_cast<float4*>(smem + kOffM2);
-    float* sB1 = reinterpret_cast<float*>(smem + kOffB1);
-    float2* sB3W4 = reinterpret_cast<float2*>(smem + kOffB3W4);
-    float* sRed = reinterpret_cast<float*>(smem + kOffRed);
-    float* sMisc = reinterpret_cast<float*>(smem + kOffMisc);
-    uint8_t* a_hi = smem + kOffAHi;
-    uint8_t* a_lo = smem + kOffALo;
+    const uint32_t sM2 = sbase + kOffM2, sB1 = sbase + kOffB1, sB3W4 = sbase + kOffB3W4;
+    const uint32_t sRed = sbase + kOffRed, sMisc = sbase + kOffMisc, sPts = sbase + kOffPts;
+    const uint32_t a_hi = sbase + kOffAHi, a_lo = sbase + kOffALo;
     const float* sparams = reinterpret_cast<const float*>(a.stat + kWeightBytes);
     uint32_t tphase = 0;                       // bit per TMEM buffer
     auto wait_tmem = [&](int buf) {
@@ -330,145 +368,170 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       tphase ^= 1u << buf;
       tc_fence_after();
     };
-    // publish "my rows of A slot s are written" to the leader's barrier
-    auto publish = [&](int s) {
+    // publish "this warp's share of A slot s is written": every slot phase collects 16 arrivals
+    // (x1: 1 warp x 2 CTAs x 8 lanes;  x2 / x3: 4 warps x 2 CTAs x 2 lanes)
+    auto publish = [&](int s, int lanes) {
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar(kBarAFull + s), 0);
+      if (lane < lanes) mbar_arrive_cluster(bar(kBarAFull + s), 0);
     };
-    auto load_params = [&](int dec, int which) {
-      // which: 0 = M0B0, 1 = b1 + M2B2, 2 = b3w4 + scalars.  All 256 epilogue threads cooperate.
+    // the 8 KiB buffer sM2 is time-shared: (M0,B0) rows during x1 generation, (M2,B2) afterwards
+    auto load_m0 = [&](int dec) {
+      const float4* g4 = reinterpret_cast<const float4*>(a.samp + (size_t)dec * kSampleFloatsPerDecoder);
+      sts_f4(sM2 + 16 * et, __ldg(g4 + et)); sts_f4(sM2 + 16 * (et + 256), __ldg(g4 + et + 256));
+    };
+    auto load_params = [&](int dec) {
+      // b1 + M2B2 + (b3,w4) + scalars of decoder `dec`; all 256 epilogue threads cooperate
       const float* samp = a.samp + (size_t)dec * kSampleFloatsPerDecoder;
       const float* sp = sparams + (size_t)dec * kStaticParamFloats;
-      if (which == 0) {
-        const float4* g = reinterpret_cast<const float4*>(samp);
-        sM0[et] = __ldg(g + et); sM0[et + 256] = __ldg(g + et + 256);
-      } else if (which == 1) {
-        const float4* g = reinterpret_cast<const float4*>(samp + 2048);
-        sM2[et] = __ldg(g + et); sM2[et + 256] = __ldg(g + et + 256);
-        sB1[et] = __ldg(sp + et);
-      } else {
-        const float2* g = reinterpret_cast<const float2*>(sp + 256);
-        sB3W4[et] = __ldg(g + et); sB3W4[et + 256] = __ldg(g + et + 256);
-        if (et < 8) sMisc[et] = __ldg(sp + 256 + 1024 + et);
+      const float4* g4 = reinterpret_cast<const float4*>(samp + 2048);
+      sts_f4(sM2 + 16 * et, __ldg(g4 + et)); sts_f4(sM2 + 16 * (et + 256), __ldg(g4 + et + 256));
+      sts_f1(sB1 + 4 * et, __ldg(sp + et));
+      const float2* g2 = reinterpret_cast<const float2*>(sp + 256);
+      sts_f2(sB3W4 + 8 * et, __ldg(g2 + et)); sts_f2(sB3W4 + 8 * (et + 256), __ldg(g2 + et + 256));
+      if (et < 8) sts_f1(sMisc + 4 * et, __ldg(sp + 256 + 1024 + et));
+    };
+    auto point_of = [&](int64_t i, float& x, float& y, float& z) {
+      x = y = z = 0.f;
+      if (i < a.q.end) {
+        if (a.q.mode == ASDF_QUERY_POINTS) {
+          const float* r = a.q.points_dev + (size_t)i * a.q.point_stride;
+          x = __ldg(r); y = __ldg(r + 1); z = __ldg(r + 2);
+        } else {
+          grid_point(i, a.q.N, a.q.mode, a.q.voxel, a.q.origin[0], a.q.origin[1], a.q.origin[2], x, y, z);
+        }
       }
     };
 
+    long long ph[12];
+    for (int z = 0; z < 12; ++z) ph[z] = 0;
+    const bool stamp = a.dbg != nullptr && cluster_id == 0 && rank == 0 && et == 0;
+#define ASDF_STAMP(k) do { if (stamp) { const long long _t = clock64(); ph[k] += _t - tlast; tlast = _t; } } while (0)
+    long long tlast = clock64();
+    load_m0(0);                                // first work item; later ones are prefetched in the layer-3 epilogue
     for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-      const int64_t i = a.q.begin + t * kPtsPerTile + rank * kPtsPerCta + row;
+      const int64_t ibase = a.q.begin + t * kPtsPerTile + rank * kPtsPerCta;
+      const int64_t i = ibase + row;
       const bool live = i < a.q.end;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (live) {
-        if (a.q.mode == ASDF_QUERY_POINTS) {
-          const float* r = a.q.points_dev + (size_t)i * a.q.point_stride;
-          px = __ldg(r); py = __ldg(r + 1); pz = __ldg(r + 2);
-        } else {
-          grid_point(i, a.q.N, a.q.mode, a.q.voxel, a.q.origin[0], a.q.origin[1], a.q.origin[2], px, py, pz);
-        }
-      }
-      float sdf_hand = 1.f;
+      float px, py, pz;
+      point_of(i, px, py, pz);                 // point of this thread's TMEM lane
+      epi_bar_sync();                          // previous tile's x1 generation is done with sPts
+      if (et < kPtsPerCta) sts_f4(sPts + 16 * et, make_float4(px, py, pz, 0.f));   // row == et for warps 4,5
+      epi_bar_sync();
       for (int dec = 0; dec < 2; ++dec) {
         // ---------------- x1 = relu(M0 p + B0) -> A slots 0..7 ----------------
-        epi_bar_sync();                       // previous users of the parameter buffers are done
-        load_params(dec, 0);
-        epi_bar_sync();
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int s = cbase + 4 * half;     // K chunk == A slot
-#pragma unroll 1
-          for (int k8 = 0; k8 < 8; ++k8) {
+        // warp e owns A slot e (64 features); a lane owns 8 of them (one 16-byte chunk) for all rows.
+        // Its 8 (M0,B0) rows stay in registers; the rows' points come from shared memory.
+        {
+          float4 m[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = lds_f4(sM2 + 16 * (e * 64 + (lane & 7) * 8 + j));
+#pragma unroll 2
+          for (int it = 0; it < 16; ++it) {
+            const int r = (lane >> 3) + 4 * it;
+            const float4 p = lds_f4(sPts + 16 * r);
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 m = sM0[s * 64 + k8 * 8 + j];
-              v[j] = fmaxf(fmaf(m.x, px, fmaf(m.y, py, fmaf(m.z, pz, m.w))), 0.f);
-            }
-            split8_store(a_hi + s * kASlotBytes, a_lo + s * kASlotBytes, row, k8, v);
+            for (int j = 0; j < 8; ++j)
+              v[j] = fmaxf(fmaf(m[j].x, p.x, fmaf(m[j].y, p.y, fmaf(m[j].z, p.z, m[j].w))), 0.f);
+            split8_store(a_hi + e * kASlotBytes, a_lo + e * kASlotBytes, r, lane & 7, v);
           }
-          publish(s);
+          publish(e, 8);
         }
-        load_params(dec, 1);
-        load_params(dec, 2);
+        ASDF_STAMP(1);
+        epi_bar_sync();                       // everybody is done with the previous decoder's parameters
+        load_params(dec);
         epi_bar_sync();
-        const float inv1 = sMisc[1], inv2 = sMisc[2], inv3 = sMisc[3], b4 = sMisc[0];
+        const float inv1 = lds_f1(sMisc + 4), inv2 = lds_f1(sMisc + 8), inv3 = lds_f1(sMisc + 12), b4 = lds_f1(sMisc);
         // ---------------- layer-1 epilogue: x2 -> A slots 0..3 ----------------
+        ASDF_STAMP(2);
         wait_tmem(0);
-        {
-          const int s = cbase;
+        ASDF_STAMP(3);
 #pragma unroll 1
-          for (int c32 = 0; c32 < 2; ++c32) {
-            float acc[32];
-            tmem_ld32(tmem_base + lane_addr + 0 * 128 + ch * 64 + c32 * 32, acc);
-            tmem_ld_wait();
+        for (int cc = 0; cc < 2; ++cc) {        // chunk inside this lane quadrant's n-half
+          const int s = nhalf * 2 + cc;
+          const int col0 = cc * 64 + ch * 32;   // this warp's 32 columns of the chunk
+          float acc[32];
+          tmem_ld32(tmem_base + lane_addr + 0 * 128 + col0, acc);
+          tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                v[j] = fmaxf(fmaf(acc[g * 8 + j], inv1, sB1[cbase * 64 + c32 * 32 + g * 8 + j]), 0.f);
-              split8_store(a_hi + s * kASlotBytes, a_lo + s * kASlotBytes, row, c32 * 4 + g, v);
-            }
+            for (int j = 0; j < 8; ++j)
+              v[j] = fmaxf(fmaf(acc[g * 8 + j], inv1, lds_f1(sB1 + 4 * (nhalf * 128 + col0 + g * 8 + j))), 0.f);
+            split8_store(a_hi + s * kASlotBytes, a_lo + s * kASlotBytes, row, ch * 4 + g, v);
           }
-          publish(s);
+          publish(s, 2);
         }
         // ---------------- layer-2 epilogue: x3 -> A slots 4..7 (nb=0), 0..3 (nb=1) ----------------
+        ASDF_STAMP(4);
 #pragma unroll 1
         for (int nb = 0; nb < 2; ++nb) {
           wait_tmem(1 + nb);
-          const int s = nb == 0 ? 4 + cbase : cbase;
+          ASDF_STAMP(5);
 #pragma unroll 1
-          for (int c32 = 0; c32 < 2; ++c32) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int s = (nb == 0 ? 4 : 0) + nhalf * 2 + cc;
+            const int col0 = cc * 64 + ch * 32;
             float acc[32];
-            tmem_ld32(tmem_base + lane_addr + (1 + nb) * 128 + ch * 64 + c32 * 32, acc);
+            tmem_ld32(tmem_base + lane_addr + (1 + nb) * 128 + col0, acc);
             tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 m = sM2[nb * 256 + cbase * 64 + c32 * 32 + g * 8 + j];
+                const float4 m = lds_f4(sM2 + 16 * (nb * 256 + nhalf * 128 + col0 + g * 8 + j));
                 const float pt = fmaf(m.x, px, fmaf(m.y, py, fmaf(m.z, pz, m.w)));
                 v[j] = fmaxf(fmaf(acc[g * 8 + j], inv2, pt), 0.f);
               }
-              split8_store(a_hi + s * kASlotBytes, a_lo + s * kASlotBytes, row, c32 * 4 + g, v);
+              split8_store(a_hi + s * kASlotBytes, a_lo + s * kASlotBytes, row, ch * 4 + g, v);
             }
+            publish(s, 2);
           }
-          publish(s);
+          ASDF_STAMP(6);
         }
         // ---------------- layer-3 epilogue: partial dot with w4 ----------------
+        epi_bar_sync();                       // every warp is done with (M2,B2): prefetch the next item's (M0,B0)
+        load_m0(dec ^ 1);
         float part = 0.f;
 #pragma unroll 1
         for (int nb = 0; nb < 2; ++nb) {
           const int buf = nb == 0 ? 3 : 0;
           wait_tmem(buf);
+          ASDF_STAMP(7);
 #pragma unroll 1
-          for (int c32 = 0; c32 < 2; ++c32) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int col0 = cc * 64 + ch * 32;
             float acc[32];
-            tmem_ld32(tmem_base + lane_addr + buf * 128 + ch * 64 + c32 * 32, acc);
+            tmem_ld32(tmem_base + lane_addr + buf * 128 + col0, acc);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float2 bw = sB3W4[nb * 256 + cbase * 64 + c32 * 32 + j];
+              const float2 bw = lds_f2(sB3W4 + 8 * (nb * 256 + nhalf * 128 + col0 + j));
               part = fmaf(fmaxf(fmaf(acc[j], inv3, bw.x), 0.f), bw.y, part);
             }
           }
+          ASDF_STAMP(8);
         }
         tc_fence_before();
-        sRed[(nhalf * 2 + ch) * 64 + row] = part;
+        sts_f1(sRed + 4 * ((nhalf * 2 + ch) * 64 + row), part);
         epi_bar_sync();
         if (et < kPtsPerCta) {
           // threads 0..63 are warps 4,5: row == et for them (q = 0,1 -> rows 0..31, 32..63)
-          const float s4 = sRed[et] + sRed[64 + et] + sRed[128 + et] + sRed[192 + et];
+          const float s4 = lds_f1(sRed + 4 * et) + lds_f1(sRed + 4 * (64 + et)) + lds_f1(sRed + 4 * (128 + et)) +
+                           lds_f1(sRed + 4 * (192 + et));
           const float val = tanhf(s4 + b4);
-          if (dec == 0) sdf_hand = val;
           if (live) (dec == 0 ? a.out_hand : a.out_obj)[i - a.q.begin] = val;
           if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> dec & 1))
             bbox_update(a.bbox + 6 * dec, live && val < 0.f, i, a.q.N);
         }
+        ASDF_STAMP(9);
       }
-      (void)sdf_hand;
     }
+    if (stamp) for (int z = 0; z < 12; ++z) a.dbg[4 + z] = ph[z];
   }
 
   // ---------------------------------- teardown ----------------------------------
@@ -489,9 +552,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_selftest_kernel(const __half* __restrict__ a_rows, const uint8_t* __restrict__ b_tiles, float* __restrict__ d_out) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   auto bar = [&](int i) { return sbase + kOffBar + 8 * i; };
@@ -499,7 +562,7 @@ tc_selftest_kernel(const __half* __restrict__ a_rows, const uint8_t* __restrict_
   if (warp == 1 && lane == 0) {
     mbar_init(bar(kBarFull), 2);
     mbar_init(bar(kBarFullLocal), 1);
-    mbar_init(bar(kBarAFull), 4);
+    mbar_init(bar(kBarAFull), 8);      // 4 staging warps x 2 CTAs
     mbar_init(bar(kBarTmemFull), 1);
     fence_mbar_init();
   }
@@ -544,12 +607,12 @@ tc_selftest_kernel(const __half* __restrict__ a_rows, const uint8_t* __restrict_
       for (int k8 = ch * 4; k8 < ch * 4 + 4; ++k8) {
         const uint4 v = *reinterpret_cast<const uint4*>(a_rows + (size_t)(rank * 64 + row) * 64 + k8 * 8);
         const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((k8 ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(smem + kOffAHi + off) = v;
+        sts_u4(sbase + kOffAHi + off, v);
       }
     }
     fence_async_smem();
     __syncwarp();
-    if (lane == 0 && nhalf == 0) mbar_arrive_cluster(bar(kBarAFull), 0);   // 2 warps x 2 CTAs = 4 arrivals
+    if (lane == 0 && nhalf == 0) mbar_arrive_cluster(bar(kBarAFull), 0);   // 4 warps x 2 CTAs = 8 arrivals
     mbar_wait(bar(kBarTmemFull), 0);
     tc_fence_after();
     for (int c32 = 0; c32 < 2; ++c32) {
@@ -603,6 +666,7 @@ extern "C" int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, co
   tc::Args a;
   a.d = *desc; a.q = *q; a.stat = (const uint8_t*)static_dev; a.samp = sample_dev;
   a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.bbox = bbox_dev;
+  a.dbg = (long long*)desc->debug_dev;
   tc::tc_eval_kernel<<<(unsigned)(2 * clusters), tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(a);
   ASDF_CUDA_CHECK(cudaGetLastError());
   return ASDF_OK;

@@ -170,4 +170,5 @@ def bind(engine, branches) -> TcBound:
             d.w_scale[b][l] = float(engine.tc_scales[b][l])
     d.act_scale = ACT_SCALE
     d.branch_stride = 2 * TILES_PER_DECODER * TILE_BYTES
+    d.debug_dev = None
     return TcBound(d, torch.from_numpy(samp).to(engine.device, non_blocking=True))

@@ -81,6 +81,7 @@ typedef struct {
   float act_scale;         /* power of two applied to activations before the fp16 split */
   float w_scale[2][3];     /* power of two applied to the weights of layers 1..3, per branch */
   int64_t branch_stride;   /* bytes between the two branches' packed weight streams */
+  void* debug_dev;         /* NULL, or int64[16] receiving phase cycle counters of CTA pair 0 */
 } asdf_tc_desc;
 int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* sample_dev,
                  const asdf_query* q, float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev,

@@ -1,0 +1,32 @@
+"""Race hunting: run the tcgen05 kernel many times on several sizes; every run must be bit-identical
+to the first one and within 2e-6 of the generic fp32 kernel."""
+import sys
+
+import torch
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from alignsdf_b200 import engine, synthetic  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+dev = torch.device("cuda")
+dec = synthetic.make_decoder(0)
+bad = 0
+for seed in range(2):
+    s = synthetic.make_sample(seed).to(dev)
+    bound = engine.get_engine(dec, dev).bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    for N in (24, 40, 64, 96):
+        hs, os_, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="simt")
+        ref = None
+        for r in range(reps):
+            h, o, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="tc")
+            torch.cuda.synchronize()
+            eh, eo = float((h - hs).abs().max()), float((o - os_).abs().max())
+            if ref is None:
+                ref = (h.clone(), o.clone())
+            same = torch.equal(h, ref[0]) and torch.equal(o, ref[1])
+            if eh > 2e-6 or eo > 2e-6 or not same:
+                bad += 1
+                nbad = int(((h - hs).abs() > 2e-6).sum()) + int(((o - os_).abs() > 2e-6).sum())
+                idx = torch.nonzero((h - hs).abs() > 2e-6)[:4, 0].tolist()
+                print(f"seed {seed} N {N} rep {r}: err hand {eh:.3e} obj {eo:.3e} identical={same} nbad={nbad} first idx {idx}")
+print("bad runs:", bad)
