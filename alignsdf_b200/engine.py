@@ -219,7 +219,7 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
                    "asdf_mc_count")
         LAUNCHES["count"] += 5
         nv, nt, mn, mx = (int(x) for x in totals.cpu())
-        if not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
+        if check_range and not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
             raise ValueError("Surface level must be within volume data range.")
         verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
         points = torch.empty((nv, 3), dtype=torch.float32, device=dev)
