@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
-from .trimesh_lite import Mesh, split as _split
+from .trimesh_lite import Mesh, largest_watertight_component_mc, split as _split
 
 INT_MAX = 2 ** 31 - 1
 
@@ -110,15 +110,8 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
         mesh_points = mesh_points * scale
     if offset is not None:
         mesh_points = mesh_points + offset
-    source_mesh = Mesh(mesh_points, faces, process=False)
-    pieces = _split(source_mesh)                           # watertight components, :372
-    if len(pieces) > 1:
-        max_area, final_mesh = -1, pieces[0]
-        for per_mesh in pieces:
-            a = per_mesh.area
-            if a > max_area:
-                max_area, final_mesh = a, per_mesh
-        source_mesh = final_mesh
+    # trimesh.graph.split + "largest area piece if more than one" (:371-381), O(V+F) fast path
+    source_mesh = largest_watertight_component_mc(mesh_points, faces, verts, vol.shape, [vs] * 3)
     source_mesh.export(ply_filename_out)
     res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
     return res + (source_mesh,) if return_mesh else res

@@ -170,7 +170,7 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     initialised process group; rank 0 writes the files and returns the meshes)."""
     import logging
     from . import engine
-    from .mesh import Mesh, _split
+    from .trimesh_lite import largest_watertight_component_mc
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = engine._device_of(latent_vec)
     bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
@@ -188,10 +188,7 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
             continue
         if tag == "obj" and hand_branch:
             points = points * np.array([1]) + np.array([0, 0, 0])      # utils/mesh.py:366-369, hand's values
-        m = Mesh(points, faces)
-        pieces = _split(m)
-        if len(pieces) > 1:
-            m = max(pieces, key=lambda x: x.area)
+        m = largest_watertight_component_mc(points, faces, verts, (N, N, N), [float(fields["voxel"])] * 3)
         if write:
             m.export(f"{filename}_{tag}.ply")
         result[tag] = m

@@ -92,3 +92,57 @@ def split(mesh: Mesh, only_watertight=True):
         used, inv = np.unique(sub, return_inverse=True)
         out.append(Mesh(mesh.vertices[used], inv.reshape(-1, 3).astype(faces.dtype)))
     return out
+
+
+def largest_watertight_component_mc(points, faces, verts_local, dims, spacing):
+    """Fast path of utils/mesh.py:371-381 for meshes produced by the marching-cubes kernel.
+
+    Same outcome as ``split`` + "keep the max-area piece iff more than one piece" but O(V+F):
+    a marching-cubes mesh is a closed manifold except where it leaves the volume, so a component
+    is watertight iff none of its triangle edges lies in a boundary plane of the volume (both end
+    points on the same plane; ``verts_local`` are the raw grid-local vertices, ``dims`` the volume
+    shape, ``spacing`` the voxel size -- lattice planes are hit exactly in float32).
+    Returns a Mesh (the input mesh when there are fewer than two watertight pieces)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    faces = np.asarray(faces).reshape(-1, 3)
+    V, F = len(points), len(faces)
+    whole = Mesh(points, faces)
+    if F == 0:
+        return whole
+    a, b, c = faces[:, 0], faces[:, 1], faces[:, 2]
+    g = coo_matrix((np.ones(2 * F, np.int8), (np.concatenate([a, b]), np.concatenate([b, c]))), shape=(V, V))
+    n, vlabel = connected_components(g, directed=False)
+    if n <= 1:
+        return whole
+    flabel = vlabel[a]
+    vl = np.asarray(verts_local, np.float32)
+    on = np.zeros(V, np.uint8)                     # bit 2k: on plane index 0 of axis k, bit 2k+1: on the last plane
+    for k in range(3):
+        on |= (vl[:, k] == 0.0).astype(np.uint8) << (2 * k)
+        on |= (vl[:, k] == np.float32(float(dims[k] - 1) * float(spacing[k]))).astype(np.uint8) << (2 * k + 1)
+    fa, fb, fc = on[a], on[b], on[c]
+    open_face = ((fa & fb) | (fb & fc) | (fc & fa)) != 0
+    is_open = np.bincount(flabel, weights=open_face, minlength=n) > 0
+    nfaces = np.bincount(flabel, minlength=n)
+    cand = np.nonzero(~is_open & (nfaces >= 4))[0]
+    if len(cand) <= 1:
+        return whole
+    v = np.asarray(points, np.float64)
+    e1, e2 = v[b] - v[a], v[c] - v[a]
+    cx = e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1]
+    cy = e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2]
+    cz = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.sqrt(cx * cx + cy * cy + cz * cz)
+    comp_area = np.bincount(flabel, weights=area, minlength=n)
+    # trimesh orders the pieces by their first face; the reference keeps the first maximum
+    first_face = np.full(n, F, np.int64)
+    ul, ui = np.unique(flabel, return_index=True)
+    first_face[ul] = ui
+    cand = cand[np.argsort(first_face[cand], kind="stable")]
+    best = cand[int(np.argmax(comp_area[cand]))]
+    sel = faces[flabel == best]
+    used = np.zeros(V, bool)
+    used[sel.reshape(-1)] = True
+    remap = np.cumsum(used) - 1
+    return Mesh(np.asarray(points)[used], remap[sel].astype(faces.dtype))

@@ -192,3 +192,22 @@ def test_trimesh_lite_split_and_ply_roundtrip(tmp_path):
     assert np.array_equal(rv, v2.astype(np.float32)) and np.array_equal(rf, f2)
     open_mesh = trimesh_lite.Mesh(v, f[:-3])             # punch a hole: no longer watertight
     assert len(trimesh_lite.split(open_mesh)) == 1
+
+
+def test_fast_component_filter_matches_generic_split():
+    """trimesh_lite.largest_watertight_component_mc (O(V+F), MC meshes only) == generic split + max area."""
+    ax = np.linspace(-1, 1, 40, dtype=np.float32)
+    x, y, z = np.meshgrid(ax, ax, ax, indexing="ij")
+    sph = lambda c, r: np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) - np.float32(r)
+    sp = 2 / 39
+    cases = [np.minimum.reduce([sph((-0.4, 0, 0), 0.33), sph((0.5, 0.1, 0), 0.25), sph((0, 0.95, 0), 0.3),
+                                sph((0, -0.6, 0.6), 0.12)]),        # one piece is cut by the volume boundary
+             sph((0, 0, 0), 0.5),                                   # single closed piece
+             sph((0, 0.95, 0), 0.3),                                # single open piece
+             np.minimum(sph((0.97, 0, 0), 0.3), sph((-0.3, 0, 0), 0.2))]   # open + closed -> one candidate -> whole
+    for vol in cases:
+        v, f, _ = mo.marching_cubes(vol, 0.0, [sp] * 3)
+        pts = (np.float32(-1) + v).astype(np.float32)
+        m = trimesh_lite.largest_watertight_component_mc(pts, f, v, vol.shape, [sp] * 3)
+        ev, ef = mo.largest_component_if_split(pts, f)
+        assert np.array_equal(m.vertices, ev) and np.array_equal(m.faces, ef)
