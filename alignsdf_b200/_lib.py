@@ -66,6 +66,10 @@ def lib():
     L.asdf_simt_eval.argtypes = [C.POINTER(SimtDesc), vp, vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp]
     L.asdf_tc_eval.restype = C.c_int
     L.asdf_tc_eval.argtypes = [C.POINTER(TcDesc), vp, vp, C.POINTER(Query), vp, vp, i32p, vp]
+    L.asdf_tc2_eval.restype = C.c_int
+    L.asdf_tc2_eval.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, vp]
+    L.asdf_tc2_static_bytes.restype = C.c_int64
+    L.asdf_tc2_sample_bytes.restype = C.c_int64
     L.asdf_tc_selftest.restype = C.c_int
     L.asdf_tc_selftest.argtypes = [vp, vp, vp, vp]
     L.asdf_tc_static_bytes.restype = C.c_int64

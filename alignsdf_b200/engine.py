@@ -17,6 +17,7 @@ from . import _lib, packer
 from ._lib import AsdfError
 
 INT_MAX = 2 ** 31 - 1
+DEFAULT_TC_PATH = "tc2"           # which tensor-core kernel "auto" prefers ("tc" = k1_tc.cu, "tc2" = k1_tc2.cu)
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
@@ -62,12 +63,28 @@ class BoundSample:
                     d.table[b][l][k] = int(pack.table[b, l, k])
         self.simt_desc = d
         self.tc = None
+        self.tc2 = None
+        self._branches = branches
         if not feature_mode and engine.tc_supported:
             from . import tc_pack
             self.tc = tc_pack.bind(engine, branches)
 
+    def _tc2_for(self, p_absmax: float):
+        """Per-sample block of the v2 tensor-core kernel, valid for |xyz| <= p_absmax (the point
+        operand scale is baked into it); returns None when the fp16 ranges cannot be met."""
+        if self.feature_mode or not self.engine.tc_supported:
+            return None
+        need = max(2.0, float(p_absmax) * 1.01)
+        if self.tc2 is None or self.tc2.info["p_absmax"] < need:
+            from . import tc2_pack
+            try:
+                self.tc2 = tc2_pack.bind(self.engine, self._branches, need)
+            except ValueError:
+                return None
+        return self.tc2
+
     # ------------------------------------------------------------------
-    def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str):
+    def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str, p_absmax: float = 2.0):
         dev = self.device
         hand = torch.empty(n, dtype=torch.float32, device=dev)
         two = self.simt_desc.n_branches == 2 or self.simt_desc.n_outputs == 2
@@ -80,12 +97,28 @@ class BoundSample:
         if n == 0:                      # empty query: nothing to launch
             return hand, obj, cls, box
         L = _lib.lib()
-        use_tc = self.tc is not None and not want_cls and path in ("auto", "tc")
-        if path == "tc" and not use_tc:
-            raise AsdfError("tensor-core path requested but not available for this decoder/query")
+        # kernel choice: tensor-core kernels need the shipped topology and no class output
+        want = DEFAULT_TC_PATH if path == "auto" else path
+        tc2 = None
+        if want == "tc2":
+            tc2 = None if want_cls else self._tc2_for(p_absmax)
+            if tc2 is None:
+                if path == "tc2":
+                    raise AsdfError("tensor-core (v2) path requested but not available for this decoder/query")
+                want = "tc"
+        if want == "tc" and (self.tc is None or want_cls):
+            if path == "tc":
+                raise AsdfError("tensor-core path requested but not available for this decoder/query")
+            want = "simt"
+        use_tc2, use_tc = want == "tc2", want == "tc"
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            if use_tc:
+            if use_tc2:
+                rc = L.asdf_tc2_eval(_lib.ptr(self.engine.tc2_static), _lib.ptr(tc2.sample), C.byref(q),
+                                     _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(box), st)
+                _lib.check(rc, "asdf_tc2_eval")
+                LAUNCHES["count"] += 1
+            elif use_tc:
                 rc = L.asdf_tc_eval(C.byref(self.tc.desc), _lib.ptr(self.engine.tc_static),
                                     _lib.ptr(self.tc.sample), C.byref(q), _lib.ptr(hand),
                                     _lib.ptr(obj), _lib.ptr(box), st)
@@ -112,7 +145,9 @@ class BoundSample:
         for k in range(3):
             q.origin[k] = float(origin[k])
         q.points_dev, q.point_stride, q.bbox_mask = None, 0, int(bbox_mask)
-        return self._run(q, end - begin, want_cls, bbox_mask != 0, path or self.engine.path)
+        # bound on |xyz| over the (possibly sheared: up to one extra voxel) lattice
+        pmax = max(max(abs(float(origin[k])), abs(float(origin[k]) + (N + 1) * float(voxel))) for k in range(3))
+        return self._run(q, end - begin, want_cls, bbox_mask != 0, path or self.engine.path, pmax)
 
     def eval_points(self, points: torch.Tensor, want_cls=False, path=None):
         """points: CUDA f32 [P, stride]; xyz rows, or embedded feature rows in feature mode."""
@@ -122,7 +157,11 @@ class BoundSample:
         q.mode, q.N, q.begin, q.end = _lib.QUERY_POINTS, 0, 0, int(pts.shape[0])
         q.voxel = 0.0
         q.points_dev, q.point_stride, q.bbox_mask = pts.data_ptr(), int(pts.shape[1]), 0
-        hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, path or self.engine.path)
+        pth = path or self.engine.path
+        pmax = 2.0
+        if pts.shape[0] and not self.feature_mode and pth in ("auto", "tc2") and self.engine.tc_supported:
+            pmax = float(pts[:, :3].abs().max())
+        hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, pth, pmax)
         return hand, obj, cls
 
 
@@ -140,12 +179,15 @@ class DecoderEngine:
                 np.concatenate([Wc, bc[:, None]], 1).astype(np.float32)).to(self.device)
         self.path = os.environ.get("ALIGNSDF_B200_PATH", "auto")
         self.tc_static = None
+        self.tc2_static = None
         self.tc_supported = False
         try:
             from . import tc_pack
             self.tc_supported = tc_pack.supported(self.topo) and _lib.lib().asdf_tc_static_bytes() > 0
             if self.tc_supported:
                 self.tc_static = tc_pack.pack_static(self)
+                from . import tc2_pack
+                self.tc2_static = tc2_pack.pack_static(self)
         except ImportError:
             self.tc_supported = False
 

@@ -86,6 +86,15 @@ typedef struct {
 int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* sample_dev,
                  const asdf_query* q, float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev,
                  void* stream);
+/* Second-generation tensor-core path (csrc/k1_tc2.cu): 128 points per CTA, activation hi-halves in
+ * tensor memory, biases / point terms folded into K=16 UMMAs.  Same outputs as asdf_tc_eval.
+ * static_dev: asdf_tc2_static_bytes() bytes, sample_dev: asdf_tc2_sample_bytes() bytes
+ * (layouts in alignsdf_b200/tc2_pack.py). */
+int asdf_tc2_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                  float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream);
+int64_t asdf_tc2_static_bytes(void);
+int64_t asdf_tc2_sample_bytes(void);
+
 /* Layout self test of the tensor-core path: D[128,256] = A[128,64] . B[256,64]^T through the same
  * operand layouts / descriptors / TMEM read-back as asdf_tc_eval (a_rows_dev fp16 row-major,
  * b_tiles_dev two pre-swizzled 16 KiB tiles, d_out_dev f32). */

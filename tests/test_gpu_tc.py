@@ -67,3 +67,44 @@ def test_tc_matches_generic_fp32_kernel_and_is_deterministic():
     hp, op, _ = bound.eval_points(xyz, path="tc")
     hq, oq, _ = bound.eval_points(xyz, path="simt")
     assert (hp - hq).abs().max() <= 2e-6 and (op - oq).abs().max() <= 2e-6
+
+
+V2_CASES = ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_hand6_n12", "sep_obj6_n12",
+            "sep_both54_n12", "sep_both9_n32_handonly", "sep_both9_n20_objonly"]
+
+
+@pytest.mark.parametrize("name", V2_CASES)
+def test_tc2_two_pass_fields_match_reference_golden(name):
+    meta, g, dec, sample = helpers.load_case(name)
+    s = helpers.to_cuda(sample)
+    hb, ob = meta.get("hand_branch", True), meta.get("obj_branch", True)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob, path="tc2")
+    assert np.float32(float(vols["voxel"])) == g["new_voxel"]
+    assert np.array_equal(vols["origin"].numpy(), g["new_origin"])
+    for key, vol in (("pass1_hand", vols["pass1_hand"]), ("pass1_obj", vols["pass1_obj"]),
+                     ("pass2_hand", vols["hand"]), ("pass2_obj", vols["obj"])):
+        if key in g:
+            err = np.abs(vol.cpu().numpy() - g[key]).max()
+            assert err <= TOL, (key, err)
+
+
+def test_tc2_matches_generic_fp32_kernel_and_is_deterministic():
+    meta, g, dec, sample = helpers.load_case("sep_both9_n24")
+    s = helpers.to_cuda(sample)
+    bound = engine.get_engine(dec, torch.device("cuda")).bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    N = 48                                    # 110592 points: 432 tiles of 256, > 5 waves of 74 CTA pairs
+    ht, ot, _, bt = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="tc2")
+    hs, os_, _, bs = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="simt")
+    assert (ht - hs).abs().max() <= 3e-6 and (ot - os_).abs().max() <= 3e-6
+    ht2, ot2, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="tc2")
+    assert torch.equal(ht, ht2) and torch.equal(ot, ot2)
+    h3, o3, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], begin=77, end=77 + 1001, path="tc2")
+    assert torch.equal(h3, ht[77:77 + 1001]) and torch.equal(o3, ot[77:77 + 1001])
+    xyz = (torch.rand(777, 3, generator=torch.Generator().manual_seed(2)) * 2 - 1).cuda()
+    hp, op, _ = bound.eval_points(xyz, path="tc2")
+    hq, oq, _ = bound.eval_points(xyz, path="simt")
+    assert (hp - hq).abs().max() <= 3e-6 and (op - oq).abs().max() <= 3e-6
+    far = xyz * 7.0                            # outside the default point-operand range: re-bound automatically
+    hp, op, _ = bound.eval_points(far, path="tc2")
+    hq, oq, _ = bound.eval_points(far, path="simt")
+    assert (hp - hq).abs().max() <= 1e-5 and (op - oq).abs().max() <= 1e-5

@@ -7,6 +7,7 @@ import torch
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from alignsdf_b200 import engine, synthetic  # noqa: E402
 
+PATH = sys.argv[2] if len(sys.argv) > 2 else "tc2"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 dev = torch.device("cuda")
 dec = synthetic.make_decoder(0)
@@ -18,7 +19,7 @@ for seed in range(2):
         hs, os_, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="simt")
         ref = None
         for r in range(reps):
-            h, o, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="tc")
+            h, o, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path=PATH)
             torch.cuda.synchronize()
             eh, eo = float((h - hs).abs().max()), float((o - os_).abs().max())
             if ref is None:
