@@ -107,6 +107,22 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b,
                "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
                :: "r"(d), "r"(a_tmem), "l"(b), "r"(kIdesc), "r"(acc), "r"(0u) : "memory");
 }
+// Lean forms used by the issuer: operands are the LOW descriptor words (address >> 4); the high
+// word (SBO = 1024 B, version 1, 128B swizzle) is the constant 0x40004040.  All operands are
+// warp-uniform so ptxas keeps them in uniform registers (no R2UR waterfall per UMMA).
+__device__ __forceinline__ void umma_ss_lo(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+               :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u) : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "mov.b64 db, {%2, %5};\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+               :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return (addr & 0x3FFFFu) >> 4; }
 __device__ __forceinline__ void umma_commit_both(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                :: "r"(bar), "h"((uint16_t)3) : "memory");
@@ -150,18 +166,20 @@ struct Args {
   float* out_hand;
   float* out_obj;
   int32_t* bbox;
+  long long* dbg;          // optional int64[32] of cycle counters of CTA pair 0 (tools/tc_phase_timing.py)
 };
 
 // N-block schedule of one work item: layer, number of 64-wide K chunks, K position of chunk j
 __device__ __forceinline__ int nb_layer(int g) { return g < 4 ? 0 : (g < 6 ? 1 : (g < 10 ? 2 : 3)); }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 0 ? 0 : (layer == 2 ? 4 : 8); }
 
+template <bool kDebug>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eval_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = blockIdx.x & 1u;          // == %cluster_ctarank for __cluster_dims__(2,1,1); provably uniform
   const bool leader = rank == 0;
   auto bar = [&](int i) { return sbase + kOffBar + 8 * i; };
 
@@ -215,9 +233,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      if (!leader) {
-        // ======================= peer CTA: relay "my half of the tile landed" =======================
+    if (!leader) {
+      // ======================= peer CTA: relay "my half of the tile landed" =======================
+      if (lane == 0) {
         uint32_t slot = 0, phase = 0;
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
           for (int i = 0; i < 2 * kTilesPerItem; ++i) {
@@ -226,64 +244,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
             if (++slot == kRing) { slot = 0; phase ^= 1; }
           }
         }
-      } else {
-        // =================================== UMMA issuer ===================================
-        uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
-        uint32_t nblk = 0;                                   // global N-block counter -> TMEM buffer + parities
-        const uint32_t a_lo = sbase + kOffALo, ring = sbase + kOffRing, ap = sbase + kOffAP;
-        auto take = [&]() {                                  // wait for the next ring tile, return its address
-          mbar_wait(bar(kBarFull + slot), phase);
-          tc_fence_after();
-          return ring + slot * kTileBytes;
-        };
-        auto release = [&]() {
-          umma_commit_both(bar(kBarEmpty + slot));
-          if (++slot == kRing) { slot = 0; phase ^= 1; }
-        };
-        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-          mbar_wait(bar(kBarApFull), ap_phase); ap_phase ^= 1;
-          tc_fence_after();
-          for (int dec = 0; dec < 2; ++dec) {
-            for (int g = 0; g < kPTilesPerDecoder; ++g, ++nblk) {
-              const int layer = nb_layer(g);
-              const bool first_nb = g == 0 || g == 4 || g == 6 || g == 10;
-              const uint32_t buf = nblk & 1u, use = nblk >> 1;
-              const uint32_t d_tmem = tmem_base + buf * 128;
-              mbar_wait(bar(kBarTmemEmpty + buf), (use & 1u) ^ 1u);
-              tc_fence_after();
-              {   // bias + point term: K = 16
-                const uint32_t b = take();
-                umma_ss(d_tmem, smem_desc(ap), smem_desc(b), 0u);
-                release();
-              }
-              const int nch = layer_chunks(layer);
-              for (int j = 0; j < nch; ++j) {
-                const int pos = layer == 3 ? ((j + 4) & 7) : j;
-                if (first_nb) {
-                  mbar_wait(bar(kBarAFull + pos), (a_phase >> pos) & 1u);
-                  a_phase ^= 1u << pos;
-                  tc_fence_after();
-                }
-                const uint32_t ahi = tmem_base + kAhiCol + pos * 32;
-                const uint32_t alo = a_lo + pos * kSlotBytes;
-                uint32_t b = take();
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts(d_tmem, ahi + ks * 8, smem_desc(b + ks * 32), 1u);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ss(d_tmem, smem_desc(alo + ks * 32), smem_desc(b + ks * 32), 1u);
-                release();
-                b = take();
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts(d_tmem, ahi + ks * 8, smem_desc(b + ks * 32), 1u);
-                release();
-              }
-              umma_commit_both(bar(kBarTmemFull + buf));
+      }
+      __syncwarp();
+    } else {
+      // =================================== UMMA issuer ===================================
+      // The whole warp walks the schedule (all values warp-uniform -> uniform registers); lane 0
+      // issues the tcgen05 instructions.
+      const bool issue = lane == 0;
+      uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
+      uint32_t nblk = 0;                                   // global N-block counter -> TMEM buffer + parities
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
+      const uint32_t alo_lo = desc_lo(sb + kOffALo), ring_lo = desc_lo(sb + kOffRing), ap_lo = desc_lo(sb + kOffAP);
+      const uint32_t bar0 = sb + kOffBar;
+      long long w_ring = 0, w_a = 0, w_acc = 0, t_begin = kDebug ? clock64() : 0;
+      auto take = [&]() -> uint32_t {                      // wait for the next ring tile, return its descriptor word
+        const long long t0 = kDebug ? clock64() : 0;
+        mbar_wait(bar0 + 8 * (kBarFull + slot), phase);
+        if (kDebug) w_ring += clock64() - t0;
+        tc_fence_after();
+        return ring_lo + slot * (kTileBytes >> 4);
+      };
+      auto release = [&]() {
+        if (issue) umma_commit_both(bar0 + 8 * (kBarEmpty + slot));
+        if (++slot == kRing) { slot = 0; phase ^= 1; }
+      };
+      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+        mbar_wait(bar0 + 8 * kBarApFull, ap_phase); ap_phase ^= 1;
+        tc_fence_after();
+        for (int dec = 0; dec < 2; ++dec) {
+          for (int g = 0; g < kPTilesPerDecoder; ++g, ++nblk) {
+            const int layer = nb_layer(g);
+            const bool first_nb = g == 0 || g == 4 || g == 6 || g == 10;
+            const uint32_t buf = nblk & 1u, use = nblk >> 1;
+            const uint32_t d_tmem = tmem_u + buf * 128;
+            {
+              const long long t0 = kDebug ? clock64() : 0;
+              mbar_wait(bar0 + 8 * (kBarTmemEmpty + buf), (use & 1u) ^ 1u);
+              if (kDebug) w_acc += clock64() - t0;
             }
+            tc_fence_after();
+            {   // bias + point term: K = 16
+              const uint32_t b = take();
+              if (issue) umma_ss_lo(d_tmem, ap_lo, b, 0u);
+              release();
+            }
+            const int nch = layer_chunks(layer);
+            for (int j = 0; j < nch; ++j) {
+              const int pos = layer == 3 ? ((j + 4) & 7) : j;
+              if (first_nb) {
+                const long long t0 = kDebug ? clock64() : 0;
+                mbar_wait(bar0 + 8 * (kBarAFull + pos), (a_phase >> pos) & 1u);
+                if (kDebug) w_a += clock64() - t0;
+                a_phase ^= 1u << pos;
+                tc_fence_after();
+              }
+              const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
+              const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
+              uint32_t b = take();
+              if (issue) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d_tmem, ahi + ks * 8, b + ks * 2, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ss_lo(d_tmem, alo + ks * 2, b + ks * 2, 1u);
+              }
+              release();
+              b = take();
+              if (issue) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d_tmem, ahi + ks * 8, b + ks * 2, 1u);
+              }
+              release();
+            }
+            if (issue) umma_commit_both(bar0 + 8 * (kBarTmemFull + buf));
           }
         }
       }
+      if (kDebug && cluster_id == 0 && issue) {
+        a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_a; a.dbg[2] = w_ring; a.dbg[3] = w_acc;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     // =================================== epilogue warps ===================================
     const int e = warp - kEpiWarp0;
@@ -334,6 +375,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
       if (lane == 0) mbar_arrive_cluster(bar(kBarTmemEmpty + (n & 1u)), 0);
     };
 
+    long long ph[16];
+    for (int z = 0; z < 16; ++z) ph[z] = 0;
+    const bool stamp = kDebug && cluster_id == 0 && rank == 0 && et == 0;
+    long long tlast = kDebug ? clock64() : 0;
+#define ASDF_STAMP2(k) do { if (stamp) { const long long _t = clock64(); ph[k] += _t - tlast; tlast = _t; } } while (0)
     for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
       const int64_t i = a.q.begin + t * kPtsPerTile + rank * kRows + row;
       const bool live = i < a.q.end;
@@ -377,7 +423,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
           const int layer = nb_layer(g);
           const int nb = g - (layer == 0 ? 0 : (layer == 1 ? 4 : (layer == 2 ? 6 : 10)));
           const uint32_t acc_addr = tmem_base + lane_addr + (nblk & 1u) * 128 + ch * 64;
+          ASDF_STAMP2(8 + layer);                 // epilogue work attributed to the previous phase of this layer
           wait_full(nblk);
+          ASDF_STAMP2(layer);                     // waiting for the accumulator of this layer
           if (layer < 3) {
             // feature chunk 2*nb + ch of the layer output -> K position of the next layer's input
             const int cidx = 2 * nb + ch;
@@ -394,7 +442,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
               split32(acc, inv, hi[h], lo[h]);
             }
             free_acc(nblk);
+            ASDF_STAMP2(8 + layer);
             if (hold) wait_full(nblk + 1);          // all UMMAs of this layer have retired
+            ASDF_STAMP2(4 + layer);
             store_half(pos, 0, hi[0], lo[0]);
             store_half(pos, 1, hi[1], lo[1]);
             publish(pos);
@@ -416,6 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
             free_acc(nblk);
           }
         }
+        ASDF_STAMP2(11);
         sts_f1(sRed + 4 * (ch * kRows + row), part);
         epi_bar_sync();
         if (ch == 0) {
@@ -424,8 +475,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
           if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> dec & 1))
             bbox_update(a.bbox + 6 * dec, live && val < 0.f, i, a.q.N);
         }
+        ASDF_STAMP2(12);
       }
     }
+    if (stamp) for (int z = 0; z < 16; ++z) a.dbg[8 + z] = ph[z];
   }
 
   tc_fence_before();
@@ -444,8 +497,18 @@ extern "C" int64_t asdf_tc2_static_bytes(void) {
 }
 extern "C" int64_t asdf_tc2_sample_bytes(void) { return asdf::tc2::kSampleBytes; }
 
+extern "C" int asdf_tc2_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                                   float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream,
+                                   void* debug_dev);
+
 extern "C" int asdf_tc2_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
                              float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream) {
+  return asdf_tc2_eval_debug(static_dev, sample_dev, q, out_hand_dev, out_obj_dev, bbox_dev, stream, nullptr);
+}
+
+extern "C" int asdf_tc2_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                                   float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream,
+                                   void* debug_dev) {
   using namespace asdf;
   ASDF_REQUIRE(static_dev && sample_dev && q && out_hand_dev && out_obj_dev, "asdf_tc2_eval: null argument");
   ASDF_REQUIRE(q->end >= q->begin, "negative query range");
@@ -458,7 +521,8 @@ extern "C" int asdf_tc2_eval(const void* static_dev, const void* sample_dev, con
   if (q->end == q->begin) return ASDF_OK;
   static bool configured = false;
   if (!configured) {
-    ASDF_CUDA_CHECK(cudaFuncSetAttribute(tc2::tc2_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes));
+    ASDF_CUDA_CHECK(cudaFuncSetAttribute(tc2::tc2_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes));
+    ASDF_CUDA_CHECK(cudaFuncSetAttribute(tc2::tc2_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes));
     configured = true;
   }
   int dev = 0, sms = 0;
@@ -469,8 +533,11 @@ extern "C" int asdf_tc2_eval(const void* static_dev, const void* sample_dev, con
   if (n_tiles < clusters) clusters = n_tiles;
   tc2::Args a;
   a.q = *q; a.stat = (const uint8_t*)static_dev; a.samp = (const uint8_t*)sample_dev;
-  a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.bbox = bbox_dev;
-  tc2::tc2_eval_kernel<<<(unsigned)(2 * clusters), tc2::kThreads, tc2::kSmemBytes, (cudaStream_t)stream>>>(a);
+  a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.bbox = bbox_dev; a.dbg = (long long*)debug_dev;
+  if (debug_dev)
+    tc2::tc2_eval_kernel<true><<<(unsigned)(2 * clusters), tc2::kThreads, tc2::kSmemBytes, (cudaStream_t)stream>>>(a);
+  else
+    tc2::tc2_eval_kernel<false><<<(unsigned)(2 * clusters), tc2::kThreads, tc2::kSmemBytes, (cudaStream_t)stream>>>(a);
   ASDF_CUDA_CHECK(cudaGetLastError());
   return ASDF_OK;
 }

@@ -92,6 +92,10 @@ int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* 
  * (layouts in alignsdf_b200/tc2_pack.py). */
 int asdf_tc2_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
                   float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream);
+/* Same, additionally filling debug_dev (int64[32]) with cycle counters of CTA pair 0. */
+int asdf_tc2_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                        float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream,
+                        void* debug_dev);
 int64_t asdf_tc2_static_bytes(void);
 int64_t asdf_tc2_sample_bytes(void);
 
