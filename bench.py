@@ -37,6 +37,20 @@ sys.path.insert(0, ROOT)
 F_MIN = 2_086_912          # algorithmic FLOP per hand+obj query after folding
 F_REF = 3_147_776          # FLOP per query as the reference executes it
 N_SAMPLES = 16             # BASELINE config #3: batch of 16 synthetic latents / poses
+NCU_TRAFFIC_BYTES = None   # filled from profiles/ by _ncu_traffic()
+
+
+def _ncu_traffic():
+    """dram bytes (read + write) per 256^3 launch of the dominant kernel, from the committed ncu summary."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_tc2_eval_256.txt")
+    if not os.path.exists(path):
+        return None
+    tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2].replace(",", "")) * unit_scale.get(f[1], 1.0)
+    return tot or None
 
 
 def measured_peaks():
@@ -264,6 +278,8 @@ def main():
     e2e_value = queries / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:
+        global NCU_TRAFFIC_BYTES
+        NCU_TRAFFIC_BYTES = _ncu_traffic() if N == 256 else None
         peaks = measured_peaks()
         line = dict(
             metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=value, unit="Mq/s",
@@ -280,8 +296,10 @@ def main():
         if world == 1 and k1_ms:
             k1 = sum(k1_ms) / len(k1_ms)
             ach = N ** 3 * F_MIN / (k1 * 1e-3) / 1e12
-            line["roofline"] = dict(bound="tensor", kernel="tc_eval_kernel", achieved=ach, peak=peaks["tflops"],
-                                    unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+            line["roofline"] = dict(bound="tensor", kernel="tc2_eval_kernel", achieved=ach, peak=peaks["tflops"],
+                                    unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=NCU_TRAFFIC_BYTES,
+                                    traffic_note="dram__bytes_read+write of one 256^3 launch, ncu --set full "
+                                                 "(profiles/r01_ncu_tc2_eval_256.txt); algorithmic HBM bytes = 8 B/query",
                                     ms_per_launch=k1, queries_per_launch=N ** 3, flop_per_query=F_MIN,
                                     issued_tflops=ach * 3 * (2 * 2 * 524288) / F_MIN,
                                     frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
