@@ -9,7 +9,7 @@ GPU, no communication).  This module adds the north star's second mode: grid axi
   pass 2   each rank evaluates its slab of the refit grid
   halo     every rank publishes its first plane (both fields)       -> ONE all_gather of [2,N,N] f32
   MC       each rank meshes [z0, z1] (its slab + the neighbour's first plane) with global keys
-  gather   vertex / face / key lists go to rank 0                   -> all_gather of counts + padded data
+  gather   vertex / face / key lists go to rank 0                   -> all_gather of counts + ONE packed gather
   stitch   rank 0 merges duplicate boundary vertices by key; the result is bit-identical to the
            single-GPU mesh (same vertex order = key order, same face order = cell order).
 
@@ -60,34 +60,67 @@ def exchange_halo(first_planes: torch.Tensor, rank: int, world: int, group=None)
     return buf[rank + 1] if rank + 1 < world else None
 
 
-def gather_varlen(t: torch.Tensor, world: int, group=None):
-    """all_gather of tensors whose first dimension differs per rank (pad to the max)."""
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    ns = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(ns, n, group=group)
-    ns = [int(x) for x in ns]
-    m = max(ns + [1])
-    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[:t.shape[0]] = t
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return [o[:k] for o, k in zip(out, ns)]
+def gather_pieces(pieces, rank: int, world: int, group=None):
+    """Gather every rank's mesh pieces on rank 0 with two collectives.
+
+    pieces: list (one per surface) of (verts [V,3] f32, faces [F,3] i32, keys [V] i64) on this rank.
+    Returns, on rank 0, a list over ranks of such lists; None elsewhere.  One all_gather of the
+    counts, then one gather of a single packed byte buffer (padded to the largest rank)."""
+    dev = pieces[0][0].device
+    counts = torch.tensor([[p[0].shape[0], p[1].shape[0]] for p in pieces], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts, group=group)
+    allc = torch.stack(allc).cpu()                              # [world, n_surfaces, 2]
+    nbytes = ((allc[:, :, 0] * (12 + 8) + allc[:, :, 1] * 12 + 7) // 8 * 8).sum(1)   # 8-byte aligned blocks
+    cap = max(int(nbytes.max()), 16)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    def as_bytes(t):
+        flat_t = torch.empty(t.numel(), dtype=t.dtype, device=t.device)     # fresh unit-stride storage
+        flat_t.copy_(t.reshape(-1))
+        return flat_t.view(torch.uint8)
+    off = 0
+    for p in pieces:                                                         # keys first (8-byte aligned)
+        for t in (p[2], p[0], p[1]):
+            b = as_bytes(t)
+            buf[off:off + b.numel()] = b
+            off += b.numel()
+        off = (off + 7) // 8 * 8
+    recv = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, recv, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = []
+    for r in range(world):
+        off, lst = 0, []
+        for s_i in range(len(pieces)):
+            nv, nf = int(allc[r, s_i, 0]), int(allc[r, s_i, 1])
+            k = recv[r][off:off + nv * 8].view(torch.int64); off += nv * 8
+            v = recv[r][off:off + nv * 12].view(torch.float32).view(nv, 3); off += nv * 12
+            f = recv[r][off:off + nf * 12].view(torch.int32).view(nf, 3); off += nf * 12
+            off = (off + 7) // 8 * 8
+            lst.append((v, f, k))
+        out.append(lst)
+    return out
 
 
 def stitch(parts):
-    """parts: per rank (verts, points, faces, keys) numpy.  Merge duplicate boundary vertices by
-    key; vertex order = key order, face order = rank (== cell) order."""
-    keys = np.concatenate([p[3] for p in parts])
-    if keys.size == 0:
-        return (np.zeros((0, 3), np.float32),) * 2 + (np.zeros((0, 3), np.int32),)
-    verts = np.concatenate([p[0] for p in parts])
-    points = np.concatenate([p[1] for p in parts])
-    uk, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    """parts: per rank (verts, faces, keys) tensors of ONE surface (any device).  Merge duplicate
+    boundary vertices by key; vertex order = key order, face order = rank (== cell) order.
+    Returns (verts [V,3] f32, faces [F,3] i32)."""
+    keys = torch.cat([p[2] for p in parts])
+    if keys.numel() == 0:
+        dev = keys.device
+        return torch.zeros((0, 3), dtype=torch.float32, device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev)
+    verts = torch.cat([p[0] for p in parts])
+    uk, inv = torch.unique(keys, sorted=True, return_inverse=True)
+    # any representative of a duplicated key will do: duplicates are bit-identical by construction
+    first = torch.empty(uk.numel(), dtype=torch.int64, device=keys.device)
+    first[inv] = torch.arange(keys.numel(), device=keys.device)
     faces, off = [], 0
     for p in parts:
-        faces.append(inv[p[2].astype(np.int64) + off])
-        off += p[3].shape[0]
-    return verts[first], points[first], np.concatenate(faces).astype(np.int32)
+        faces.append(inv[p[1].long() + off])
+        off += p[2].shape[0]
+    return verts[first], torch.cat(faces).to(torch.int32)
 
 
 def two_pass_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=True, obj_branch=True,
@@ -110,16 +143,17 @@ def two_pass_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=T
 
 
 def mesh_slab(backend: Backend, fields: dict, N: int, rank: int, world: int, which=("hand", "obj"), group=None):
-    """Halo exchange + marching cubes + gather + stitch.  Returns {tag: (verts, points, faces)} on
-    rank 0 (numpy) and None elsewhere."""
+    """Halo exchange + marching cubes + gather + stitch.  Returns {tag: (verts, points, faces)} as
+    tensors on rank 0's device (None elsewhere); points = f32(origin) + verts like utils/mesh.py:360-363."""
     z0, z1 = fields["z0"], fields["z1"]
     nz = z1 - z0
-    first = torch.stack([fields["hand"][0] if nz else torch.zeros(N, N, device=backend.device),
-                         fields["obj"][0] if nz else torch.zeros(N, N, device=backend.device)])
+    dev = backend.device
+    first = torch.stack([fields["hand"][0] if nz else torch.zeros(N, N, device=dev),
+                         fields["obj"][0] if nz else torch.zeros(N, N, device=dev)])
     halo = exchange_halo(first, rank, world, group)
     vs = float(fields["voxel"])
     org = fields["origin"].tolist()
-    out = {}
+    pieces, tags = [], []
     for ti, tag in enumerate(("hand", "obj")):
         if tag not in which:
             continue
@@ -127,19 +161,21 @@ def mesh_slab(backend: Backend, fields: dict, N: int, rank: int, world: int, whi
         if halo is not None and nz:
             vol = torch.cat([vol, halo[ti:ti + 1]], 0)
         if vol.shape[0] >= 2:
-            v, p, f, k = backend.mc(vol.contiguous(), vs, org, z0)
+            v, _, f, k = backend.mc(vol.contiguous(), vs, org, z0)
         else:
-            dev = backend.device
-            v = p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
+            v = torch.zeros((0, 3), dtype=torch.float32, device=dev)
             f = torch.zeros((0, 3), dtype=torch.int32, device=dev)
             k = torch.zeros((0,), dtype=torch.int64, device=dev)
-        gv, gp = gather_varlen(v, world, group), gather_varlen(p, world, group)
-        gf, gk = gather_varlen(f, world, group), gather_varlen(k, world, group)
-        if rank == 0:
-            parts = [(a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy(), d.cpu().numpy())
-                     for a, b, c, d in zip(gv, gp, gf, gk)]
-            out[tag] = stitch(parts)
-    return out if rank == 0 else None
+        pieces.append((v, f, k)); tags.append(tag)
+    gathered = gather_pieces(pieces, rank, world, group)
+    if rank != 0:
+        return None
+    out = {}
+    org32 = torch.tensor(org, dtype=torch.float32, device=dev)
+    for s_i, tag in enumerate(tags):
+        verts, faces = stitch([gathered[r][s_i] for r in range(world)])
+        out[tag] = (verts, org32[None] + verts, faces)
+    return out
 
 
 # ----------------------------------------------------------------------------
@@ -182,7 +218,7 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
         return None
     result = {"hand": None, "obj": None}
     for tag in which:
-        verts, points, faces = meshes[tag]
+        verts, points, faces = (x.cpu().numpy() for x in meshes[tag])
         if faces.shape[0] == 0:
             logging.warning("Cannot reconstruct mesh from '{}'".format(f"{filename}_{tag}.ply"))
             continue

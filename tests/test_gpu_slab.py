@@ -25,6 +25,7 @@ def _worker(rank, world, port, out_dir):
         if rank == 0:
             np.savez(os.path.join(out_dir, "slab.npz"), hv=res["hand"].vertices, hf=res["hand"].faces,
                      ov=res["obj"].vertices, of=res["obj"].faces)
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 

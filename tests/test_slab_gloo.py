@@ -66,7 +66,8 @@ def _worker(rank, world, port, name, out_dir):
                  origin=fields["origin"].numpy(), hand=fields["hand"].numpy(), z0=fields["z0"], z1=fields["z1"])
         if rank == 0:
             np.savez(os.path.join(out_dir, "mesh.npz"),
-                     **{f"{t}_{n}": a for t in meshes for n, a in zip(("v", "p", "f"), meshes[t])})
+                     **{f"{t}_{n}": a.numpy() for t in meshes for n, a in zip(("v", "p", "f"), meshes[t])})
+        dist.barrier()          # rank 0 may still be receiving the gathered pieces
     finally:
         dist.destroy_process_group()
 
