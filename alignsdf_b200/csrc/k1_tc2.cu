@@ -110,17 +110,24 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b,
 // Lean forms used by the issuer: operands are the LOW descriptor words (address >> 4); the high
 // word (SBO = 1024 B, version 1, 128B swizzle) is the constant 0x40004040.  All operands are
 // warp-uniform so ptxas keeps them in uniform registers (no R2UR waterfall per UMMA).
-__device__ __forceinline__ void umma_ss_lo(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+// `issue` != 0 only in the issuing lane: the instruction is predicated inside the asm, so the
+// surrounding code stays branch-free (no per-UMMA divergence handling).
+__device__ __forceinline__ void umma_ss_lo(uint32_t issue, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
                "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-               :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u) : "memory");
+               "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+               :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(issue) : "memory");
 }
-__device__ __forceinline__ void umma_ts_lo(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+__device__ __forceinline__ void umma_ts_lo(uint32_t issue, uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
                "mov.b64 db, {%2, %5};\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
-               :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(0u) : "memory");
+               "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+               :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(0u), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void umma_commit_both_if(uint32_t issue, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+               :: "r"(bar), "h"((uint16_t)3), "r"(issue) : "memory");
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return (addr & 0x3FFFFu) >> 4; }
 __device__ __forceinline__ void umma_commit_both(uint32_t bar) {
@@ -250,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
       // =================================== UMMA issuer ===================================
       // The whole warp walks the schedule (all values warp-uniform -> uniform registers); lane 0
       // issues the tcgen05 instructions.
-      const bool issue = lane == 0;
+      const uint32_t issue = lane == 0 ? 1u : 0u;
       uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
       uint32_t nblk = 0;                                   // global N-block counter -> TMEM buffer + parities
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -266,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
         return ring_lo + slot * (kTileBytes >> 4);
       };
       auto release = [&]() {
-        if (issue) umma_commit_both(bar0 + 8 * (kBarEmpty + slot));
+        umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + slot));
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       };
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
@@ -286,7 +293,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
             tc_fence_after();
             {   // bias + point term: K = 16
               const uint32_t b = take();
-              if (issue) umma_ss_lo(d_tmem, ap_lo, b, 0u);
+              umma_ss_lo(issue, d_tmem, ap_lo, b, 0u);
               release();
             }
             const int nch = layer_chunks(layer);
@@ -302,21 +309,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
               const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
               const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
               uint32_t b = take();
-              if (issue) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d_tmem, ahi + ks * 8, b + ks * 2, 1u);
+              for (int ks = 0; ks < 4; ++ks) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ss_lo(d_tmem, alo + ks * 2, b + ks * 2, 1u);
-              }
+              for (int ks = 0; ks < 4; ++ks) umma_ss_lo(issue, d_tmem, alo + ks * 2, b + ks * 2, 1u);
               release();
               b = take();
-              if (issue) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d_tmem, ahi + ks * 8, b + ks * 2, 1u);
-              }
+              for (int ks = 0; ks < 4; ++ks) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
               release();
             }
-            if (issue) umma_commit_both(bar0 + 8 * (kBarTmemFull + buf));
+            umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
           }
         }
       }
