@@ -15,8 +15,8 @@
 //   TMEM   [  0,128) ACC0   [128,256) ACC1   (fp32 accumulators of one 128-wide N block each)
 //          [256,512) AHI    fp16 pairs, column 256 + k/2 holds (k even | k odd << 16) of hi(t*x[k])
 //   SMEM   ALO  8 slots x [128 rows x 64 k] fp16 lo halves, K-major 128B swizzle       128 KiB
-//          AP   [128 rows x 64 k] point operand (cp*p_hi, c1, cp*p_lo, ...)              16 KiB
-//          RING 9 x [64 rows x 64 k] weight tiles (this CTA's half of every B tile)       72 KiB
+//          AP   [128 rows x 16 k] point operand (cp*p_hi, c1, cp*p_lo, ...), no swizzle      4 KiB
+//          RING 5 x (hi, lo) pairs of [64 rows x 64 k] weight tiles (this CTA's half)      80 KiB
 //
 // Per N block (128 output features):  UMMA(AP, Ptile)            bias + point term, K=16
 //                                     per 64-wide K chunk:  4 x UMMA(AHI, Bhi) + 4 x UMMA(ALO, Bhi)
@@ -36,18 +36,20 @@ constexpr int kRows = 128;                  // points per CTA
 constexpr int kPtsPerTile = 256;            // per CTA pair
 constexpr int kTileBytes = 64 * 64 * 2;     // weight tile: 64 rows x 64 k fp16 = 8 KiB
 constexpr int kSlotBytes = kRows * 64 * 2;  // ALO slot / AP: 128 rows x 64 k fp16 = 16 KiB
-constexpr int kRing = 9;
+constexpr int kRing = 5;                    // ring slots of one (hi, lo) tile pair each
 constexpr int kMainTilesPerDecoder = 128;   // 32 (L1) + 32 (L2) + 64 (L3)
 constexpr int kPTilesPerDecoder = 14;       // 4 (L0) + 2 (L1) + 4 (L2) + 4 (L3) N blocks
-constexpr int kTilesPerItem = kMainTilesPerDecoder + kPTilesPerDecoder;
+constexpr int kSlotTileBytes = 2 * kTileBytes;   // a ring slot holds a (hi, lo) pair (16 KiB) or one P tile
+constexpr int kFillsPerItem = kMainTilesPerDecoder / 2 + kPTilesPerDecoder;   // ring fills per work item
 constexpr int64_t kWeightBytes = (int64_t)2 * 2 * kMainTilesPerDecoder * kTileBytes;   // [dec][rank][tile]
 constexpr int kStaticParamFloats = 512 + 8;            // w4[512] | b4, inv1, inv2, inv3, pad
 constexpr int64_t kSampleBytes = (int64_t)2 * 2 * kPTilesPerDecoder * kTileBytes + 64;  // P tiles + 16 floats
 
 constexpr int kOffALo = 0;
+constexpr int kApBytes = kRows * 16 * 2;                          // point operand: 128 rows x 16 k, no swizzle (4 KiB)
 constexpr int kOffAP = kOffALo + 8 * kSlotBytes;                 // 131072
-constexpr int kOffRing = kOffAP + kSlotBytes;                    // 147456
-constexpr int kOffW4 = kOffRing + kRing * kTileBytes;            // 221184
+constexpr int kOffRing = kOffAP + kApBytes;                      // 135168 (1024-aligned)
+constexpr int kOffW4 = kOffRing + kRing * kSlotTileBytes;        // 217088
 constexpr int kOffRed = kOffW4 + 512 * 4;
 constexpr int kOffBar = kOffRed + 2 * kRows * 4;
 constexpr int kBarFull = 0;
@@ -123,6 +125,16 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t issue, uint32_t d, uint32_t 
                "mov.b64 db, {%2, %5};\n\t"
                "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
                :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(0u), "r"(issue) : "memory");
+}
+// A = point operand in the no-swizzle K-major layout: core matrices of 8 rows x 16 B, the two K
+// halves 128 B apart (LBO), 8-row groups 256 B apart (SBO); B = SW128 tile as above.
+__device__ __forceinline__ void umma_ap(uint32_t issue, uint32_t d, uint32_t ap_addr, uint32_t b_lo, uint32_t acc) {
+  const uint32_t a_lo = ((ap_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+               "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %5};\n\t"
+               "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+               :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u),
+                  "r"((256u >> 4) | (1u << 14)), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void umma_commit_both_if(uint32_t issue, uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
@@ -219,11 +231,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
     // =========================== weight-stream producer ===========================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      auto push = [&](const uint8_t* src) {
+      auto push = [&](const uint8_t* src, uint32_t bytes) {
         mbar_wait(bar(kBarEmpty + slot), phase ^ 1);
         const uint32_t fb = bar((leader ? kBarFull : kBarFullLocal) + slot);
-        mbar_expect_tx(fb, kTileBytes);
-        bulk_g2s(sbase + kOffRing + slot * kTileBytes, src, kTileBytes, fb);
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(sbase + kOffRing + slot * kSlotTileBytes, src, bytes, fb);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       };
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
@@ -231,9 +243,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
           const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * kMainTilesPerDecoder * kTileBytes;
           const uint8_t* pt = a.samp + (int64_t)(dec * 2 + rank) * kPTilesPerDecoder * kTileBytes;
           for (int g = 0; g < kPTilesPerDecoder; ++g) {
-            push(pt); pt += kTileBytes;
-            const int n = 2 * layer_chunks(nb_layer(g));
-            for (int i = 0; i < n; ++i) { push(mt); mt += kTileBytes; }
+            push(pt, kTileBytes); pt += kTileBytes;
+            const int n = layer_chunks(nb_layer(g));
+            for (int i = 0; i < n; ++i) { push(mt, kSlotTileBytes); mt += kSlotTileBytes; }   // hi + lo in one copy
           }
         }
       }
@@ -245,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
       if (lane == 0) {
         uint32_t slot = 0, phase = 0;
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-          for (int i = 0; i < 2 * kTilesPerItem; ++i) {
+          for (int i = 0; i < 2 * kFillsPerItem; ++i) {
             mbar_wait(bar(kBarFullLocal + slot), phase);
             mbar_arrive_cluster(bar(kBarFull + slot), 0);
             if (++slot == kRing) { slot = 0; phase ^= 1; }
@@ -262,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
       uint32_t nblk = 0;                                   // global N-block counter -> TMEM buffer + parities
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
-      const uint32_t alo_lo = desc_lo(sb + kOffALo), ring_lo = desc_lo(sb + kOffRing), ap_lo = desc_lo(sb + kOffAP);
+      const uint32_t alo_lo = desc_lo(sb + kOffALo), ring_lo = desc_lo(sb + kOffRing), ap_addr = sb + kOffAP;
       const uint32_t bar0 = sb + kOffBar;
       long long w_ring = 0, w_a = 0, w_acc = 0, t_begin = kDebug ? clock64() : 0;
       auto take = [&]() -> uint32_t {                      // wait for the next ring tile, return its descriptor word
@@ -270,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
         mbar_wait(bar0 + 8 * (kBarFull + slot), phase);
         if (kDebug) w_ring += clock64() - t0;
         tc_fence_after();
-        return ring_lo + slot * (kTileBytes >> 4);
+        return ring_lo + slot * (kSlotTileBytes >> 4);
       };
       auto release = [&]() {
         umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + slot));
@@ -293,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
             tc_fence_after();
             {   // bias + point term: K = 16
               const uint32_t b = take();
-              umma_ss_lo(issue, d_tmem, ap_lo, b, 0u);
+              umma_ap(issue, d_tmem, ap_addr, b, 0u);
               release();
             }
             const int nch = layer_chunks(layer);
@@ -308,15 +320,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
               }
               const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
               const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
-              uint32_t b = take();
+              const uint32_t b = take();                       // (hi, lo) tile pair
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) umma_ss_lo(issue, d_tmem, alo + ks * 2, b + ks * 2, 1u);
-              release();
-              b = take();
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
+              for (int ks = 0; ks < 4; ++ks) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + (kTileBytes >> 4) + ks * 2, 1u);
               release();
             }
             umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
@@ -404,9 +414,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc2_eva
         const __half2 lxy = __floats2half2_rn(sx - fxy.x, sy - fxy.y), lz0 = __floats2half2_rn(sz - fz, 0.f);
         const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&hxy), w1 = *reinterpret_cast<const uint32_t*>(&hz1);
         const uint32_t w2 = *reinterpret_cast<const uint32_t*>(&lxy), w3 = *reinterpret_cast<const uint32_t*>(&lz0);
-        const uint32_t base = sbase + kOffAP + (row >> 3) * 1024 + (row & 7) * 128;
-        sts_u4(base + ((0 ^ (row & 7)) << 4), make_uint4(w0, w1, w2, w3));      // k 0..7 : p_hi, c1, p_lo, 0
-        sts_u4(base + ((1 ^ (row & 7)) << 4), make_uint4(w0, w1, 0u, 0u));      // k 8..15: p_hi, c1, 0
+        const uint32_t base = sbase + kOffAP + (row >> 3) * 256 + (row & 7) * 16;
+        sts_u4(base, make_uint4(w0, w1, w2, w3));             // k 0..7 : p_hi, c1, p_lo, 0
+        sts_u4(base + 128, make_uint4(w0, w1, 0u, 0u));       // k 8..15: p_hi, c1, 0
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(bar(kBarApFull), 0);
