@@ -72,6 +72,12 @@ def lib():
     L.asdf_tc2_eval_debug.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, vp, vp]
     L.asdf_tc2_static_bytes.restype = C.c_int64
     L.asdf_tc2_sample_bytes.restype = C.c_int64
+    L.asdf_tc3_eval.restype = C.c_int
+    L.asdf_tc3_eval.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp]
+    L.asdf_tc3_eval_debug.restype = C.c_int
+    L.asdf_tc3_eval_debug.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp, vp]
+    L.asdf_tc3_static_bytes.restype = C.c_int64
+    L.asdf_tc3_sample_bytes.restype = C.c_int64
     L.asdf_tc_selftest.restype = C.c_int
     L.asdf_tc_selftest.argtypes = [vp, vp, vp, vp]
     L.asdf_tc_static_bytes.restype = C.c_int64

@@ -17,7 +17,10 @@ from . import _lib, packer
 from ._lib import AsdfError
 
 INT_MAX = 2 ** 31 - 1
-DEFAULT_TC_PATH = "tc2"           # which tensor-core kernel "auto" prefers ("tc" = k1_tc.cu, "tc2" = k1_tc2.cu)
+# which tensor-core kernel "auto" prefers: "tc3" = k1_tc3.cu (fp16 + fp8 corrections, falls back to
+# "tc2" = k1_tc2.cu (fp16 x3) when an activation leaves the fp8 operand range), "tc" = k1_tc.cu
+DEFAULT_TC_PATH = "tc3"
+FALLBACKS = {"tc3_to_tc2": 0}    # launches whose fp8 range flag fired and were re-run through k1_tc2.cu
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
@@ -64,6 +67,7 @@ class BoundSample:
         self.simt_desc = d
         self.tc = None
         self.tc2 = None
+        self.tc3 = None
         self._branches = branches
         if not feature_mode and engine.tc_supported:
             from . import tc_pack
@@ -83,6 +87,19 @@ class BoundSample:
                 return None
         return self.tc2
 
+    def _tc3_for(self, p_absmax: float):
+        """Same for the v3 kernel (its own block: activations are not pre-scaled there)."""
+        if self.feature_mode or not self.engine.tc_supported:
+            return None
+        need = max(2.0, float(p_absmax) * 1.01)
+        if self.tc3 is None or self.tc3.info["p_absmax"] < need:
+            from . import tc3_pack
+            try:
+                self.tc3 = tc3_pack.bind(self.engine, self._branches, need)
+            except ValueError:
+                return None
+        return self.tc3
+
     # ------------------------------------------------------------------
     def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str, p_absmax: float = 2.0):
         dev = self.device
@@ -99,7 +116,13 @@ class BoundSample:
         L = _lib.lib()
         # kernel choice: tensor-core kernels need the shipped topology and no class output
         want = DEFAULT_TC_PATH if path == "auto" else path
-        tc2 = None
+        tc2 = tc3 = None
+        if want == "tc3":
+            tc3 = None if want_cls else self._tc3_for(p_absmax)
+            if tc3 is None:
+                if path == "tc3":
+                    raise AsdfError("tensor-core (v3) path requested but not available for this decoder/query")
+                want = "tc2"
         if want == "tc2":
             tc2 = None if want_cls else self._tc2_for(p_absmax)
             if tc2 is None:
@@ -110,10 +133,23 @@ class BoundSample:
             if path == "tc":
                 raise AsdfError("tensor-core path requested but not available for this decoder/query")
             want = "simt"
-        use_tc2, use_tc = want == "tc2", want == "tc"
+        use_tc3, use_tc2, use_tc = want == "tc3", want == "tc2", want == "tc"
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            if use_tc2:
+            if use_tc3:
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                rc = L.asdf_tc3_eval(_lib.ptr(self.engine.tc3_static), _lib.ptr(tc3.sample), C.byref(q),
+                                     _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(box), _lib.ptr(status), st)
+                _lib.check(rc, "asdf_tc3_eval")
+                LAUNCHES["count"] += 1
+                if int(status.item()) != 0:
+                    # an activation left the range of the fp8 correction operands: the launch's outputs
+                    # (and bbox) are not trustworthy -> same query through the all-fp16 kernel
+                    if path == "tc3" and os.environ.get("ALIGNSDF_B200_STRICT_PATH"):
+                        raise AsdfError("k1_tc3: activation outside the fp8 operand range")
+                    FALLBACKS["tc3_to_tc2"] += 1
+                    return self._run(q, n, want_cls, bbox, "tc2", p_absmax)
+            elif use_tc2:
                 rc = L.asdf_tc2_eval(_lib.ptr(self.engine.tc2_static), _lib.ptr(tc2.sample), C.byref(q),
                                      _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(box), st)
                 _lib.check(rc, "asdf_tc2_eval")
@@ -159,7 +195,7 @@ class BoundSample:
         q.points_dev, q.point_stride, q.bbox_mask = pts.data_ptr(), int(pts.shape[1]), 0
         pth = path or self.engine.path
         pmax = 2.0
-        if pts.shape[0] and not self.feature_mode and pth in ("auto", "tc2") and self.engine.tc_supported:
+        if pts.shape[0] and not self.feature_mode and pth in ("auto", "tc2", "tc3") and self.engine.tc_supported:
             pmax = float(pts[:, :3].abs().max())
         hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, pth, pmax)
         return hand, obj, cls
@@ -180,6 +216,9 @@ class DecoderEngine:
         self.path = os.environ.get("ALIGNSDF_B200_PATH", "auto")
         self.tc_static = None
         self.tc2_static = None
+        self.tc3_static = None
+        self.tc2_scales = None
+        self.tc3_scales = None
         self.tc_supported = False
         try:
             from . import tc_pack
@@ -188,6 +227,8 @@ class DecoderEngine:
                 self.tc_static = tc_pack.pack_static(self)
                 from . import tc2_pack
                 self.tc2_static = tc2_pack.pack_static(self)
+                from . import tc3_pack
+                self.tc3_static = tc3_pack.pack_static(self)
         except ImportError:
             self.tc_supported = False
 

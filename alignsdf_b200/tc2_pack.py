@@ -121,15 +121,16 @@ def choose_point_scales(layer_terms, p_absmax):
     return float(cp), float(c1), S0
 
 
-def pack_sample_numpy(branches, scales, p_absmax=1.25):
-    """Per-sample block from the folded branches (packer.fold_decoder, xyz mode)."""
+def pack_sample_numpy(branches, scales, p_absmax=1.25, act_scale=ACT_SCALE):
+    """Per-sample block from the folded branches (packer.fold_decoder, xyz mode); ``act_scale`` is the
+    power of two t the kernel keeps its activations multiplied by (16 for k1_tc2.cu, 1 for k1_tc3.cu)."""
     terms = []
     for d, br in enumerate(branches):
         L = br.layers
         terms.append([(None, L[0].M.astype(np.float64), L[0].B.astype(np.float64)),
-                      (ACT_SCALE * scales[d][0], None, _pad1(L[1].B, 256)),
-                      (ACT_SCALE * scales[d][1], L[2].M.astype(np.float64), L[2].B.astype(np.float64)),
-                      (ACT_SCALE * scales[d][2], None, L[3].B.astype(np.float64))])
+                      (act_scale * scales[d][0], None, _pad1(L[1].B, 256)),
+                      (act_scale * scales[d][1], L[2].M.astype(np.float64), L[2].B.astype(np.float64)),
+                      (act_scale * scales[d][2], None, L[3].B.astype(np.float64))])
     cp, c1, S0 = choose_point_scales(terms, p_absmax)
     tiles = np.zeros((2, 2, P_TILES, TILE_ELEMS), np.float16)
     for d in range(2):
@@ -153,7 +154,7 @@ def pack_sample_numpy(branches, scales, p_absmax=1.25):
                 g += 1
         assert g == P_TILES
     scal = np.zeros(16, np.float32)
-    scal[0], scal[1] = ACT_SCALE / S0[0], ACT_SCALE / S0[1]
+    scal[0], scal[1] = act_scale / S0[0], act_scale / S0[1]
     scal[2], scal[3] = cp, c1
     return np.concatenate([tiles.reshape(-1).view(np.uint8), scal.view(np.uint8)]), dict(cp=cp, c1=c1, S0=S0)
 

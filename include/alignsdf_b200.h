@@ -99,6 +99,23 @@ int asdf_tc2_eval_debug(const void* static_dev, const void* sample_dev, const as
 int64_t asdf_tc2_static_bytes(void);
 int64_t asdf_tc2_sample_bytes(void);
 
+/* Third-generation tensor-core path (csrc/k1_tc3.cu): the asdf_tc2_eval data flow with the two
+ * split-precision correction products in fp8 (kind::f8f6f4, e4m3) -- 8 instead of 12 UMMAs per
+ * 64-wide K chunk.  Same outputs and contract (|sdf - reference| <= 1e-5).
+ * static_dev: asdf_tc3_static_bytes() bytes, sample_dev: asdf_tc3_sample_bytes() bytes (layouts in
+ * alignsdf_b200/tc3_pack.py).  status_dev: int32[1], zeroed by the caller; bit 0 is raised when an
+ * activation exceeded the range of the fp8 operands -- the outputs of that launch must then be
+ * discarded and the query re-run through asdf_tc2_eval (alignsdf_b200/engine.py does). */
+int asdf_tc3_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                  float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
+                  void* stream);
+/* Same, additionally filling debug_dev (int64[32]) with cycle counters of CTA pair 0. */
+int asdf_tc3_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
+                        float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
+                        void* stream, void* debug_dev);
+int64_t asdf_tc3_static_bytes(void);
+int64_t asdf_tc3_sample_bytes(void);
+
 /* Layout self test of the tensor-core path: D[128,256] = A[128,64] . B[256,64]^T through the same
  * operand layouts / descriptors / TMEM read-back as asdf_tc_eval (a_rows_dev fp16 row-major,
  * b_tiles_dev two pre-swizzled 16 KiB tiles, d_out_dev f32). */

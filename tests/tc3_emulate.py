@@ -1,0 +1,89 @@
+"""Numpy emulation of csrc/k1_tc3.cu's arithmetic from the *packed* buffers (test helper): fp16 main
+product with the activation hi halves, e4m3 correction products (lo8 x W8, x8 x Wl8), P tiles (bias +
+point term as a K=16 fp16 product), main tiles in stream order, position remapping of layer 3."""
+import numpy as np
+
+from alignsdf_b200 import tc3_pack as T
+
+
+def _split(v32):
+    """epilogue of layers 0..2: v -> hi16, e4m3(2^10 lo), e4m3(hi16)  (as float64 values)"""
+    v = np.maximum(v32, 0).astype(np.float32)
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float32)
+    lo8 = T.e4m3_decode(T.e4m3_encode(lo * np.float32(T.LO_SCALE)))
+    x8 = T.e4m3_decode(T.e4m3_encode(hi.astype(np.float32)))
+    return hi.astype(np.float64), lo8.astype(np.float64), x8.astype(np.float64)
+
+
+def emulate(raw_static, raw_sample, xyz, want_max=False):
+    raw_static = np.asarray(raw_static, np.uint8)
+    raw_sample = np.asarray(raw_sample, np.uint8)
+    nmain = 2 * 2 * T.MAIN_TILES * T.TILE_BYTES
+    main = raw_static[:nmain].reshape(2, 2, T.MAIN_TILES, T.TILE_BYTES)
+    params = raw_static[nmain:].view(np.float32).reshape(2, T.STATIC_PARAM_FLOATS)
+    nps = 2 * 2 * T.P_TILES * T.TILE_BYTES
+    ptiles = raw_sample[:nps].view(np.float16).reshape(2, 2, T.P_TILES, T.TILE_ELEMS)
+    scal = raw_sample[nps:].view(np.float32)
+    cp, c1 = np.float32(scal[2]), np.float32(scal[3])
+    p = np.asarray(xyz, np.float32)
+    P = p.shape[0]
+    s = (p * cp).astype(np.float32)
+    ph = s.astype(np.float16)
+    pl = (s - ph.astype(np.float32)).astype(np.float16)
+    ap = np.zeros((P, 16), np.float64)
+    ap[:, 0:3], ap[:, 3] = ph, np.float16(c1)
+    ap[:, 4:7] = pl
+    ap[:, 8:11], ap[:, 11] = ph, np.float16(c1)
+    outs = []
+    vmax = 0.0
+    for d in range(2):
+        w4, (b4, inv1, inv2, inv3) = params[d, :512], params[d, 512:516]
+        inv0 = scal[d]
+        mi = [0]
+        pi = [0]
+
+        def ptile_acc():
+            acc = np.zeros((P, 128))
+            for c in range(2):
+                tile = T.unswizzle_tile(ptiles[d, c, pi[0]]).astype(np.float64)      # [64, 64]
+                acc[:, 64 * c:64 * c + 64] = ap @ tile[:, :16].T
+            pi[0] += 1
+            return acc
+
+        def main_acc(acc, a_hi, a_lo8, a_x8, positions):
+            for pos in positions:
+                for c in range(2):
+                    bhi = T.unswizzle_tile(main[d, c, mi[0]].view(np.float16)).astype(np.float64)
+                    b8 = T.e4m3_decode(T.unswizzle_tile8(main[d, c, mi[0] + 1])).astype(np.float64)   # [64, 128]
+                    cols = slice(64 * c, 64 * c + 64)
+                    acc[:, cols] += a_hi[pos] @ bhi.T + a_lo8[pos] @ b8[:, :64].T + a_x8[pos] @ b8[:, 64:].T
+                mi[0] += 2
+            return acc
+
+        a_hi, a_lo8, a_x8 = {}, {}, {}
+
+        def store(layer_out, inv, pos_of):
+            nonlocal vmax
+            x = (layer_out.astype(np.float32) * np.float32(inv)).astype(np.float32)
+            vmax = max(vmax, float(x.max()))
+            hi, lo8, x8 = _split(x)
+            for cidx in range(x.shape[1] // 64):
+                sl = slice(64 * cidx, 64 * cidx + 64)
+                a_hi[pos_of(cidx)], a_lo8[pos_of(cidx)], a_x8[pos_of(cidx)] = hi[:, sl], lo8[:, sl], x8[:, sl]
+
+        l0 = np.concatenate([ptile_acc() for _ in range(4)], 1).astype(np.float32)
+        store(l0, inv0, lambda c: c)
+        l1 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8, range(8)) for _ in range(2)], 1).astype(np.float32)
+        store(l1, inv1, lambda c: c)
+        l2 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8, range(4)) for _ in range(4)], 1).astype(np.float32)
+        store(l2, inv2, lambda c: (c + 4) % 8)
+        l3 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8, [(j + 4) % 8 for j in range(8)])
+                             for _ in range(4)], 1)
+        assert mi[0] == T.MAIN_TILES and pi[0] == T.P_TILES
+        x4 = np.maximum(l3.astype(np.float32) * np.float32(inv3), 0).astype(np.float32)
+        s4 = (x4.astype(np.float64) @ w4.astype(np.float64)).astype(np.float32)
+        outs.append(np.tanh(s4 + b4).astype(np.float32))
+    if want_max:
+        return outs, vmax
+    return outs
