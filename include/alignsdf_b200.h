@@ -109,7 +109,7 @@ int64_t asdf_tc2_sample_bytes(void);
 int asdf_tc3_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
                   float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
                   void* stream);
-/* Same, additionally filling debug_dev (int64[32]) with cycle counters of CTA pair 0. */
+/* Same, additionally filling debug_dev (int64[512], zeroed by the caller) with cycle counters of CTA pair 0. */
 int asdf_tc3_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
                         float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
                         void* stream, void* debug_dev);

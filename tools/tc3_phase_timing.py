@@ -20,7 +20,7 @@ q = _lib.Query()
 q.mode, q.N, q.begin, q.end, q.voxel = 0, N, 0, N ** 3, 2.0 / (N - 1)
 q.origin[:] = [-1.0, -1.0, -1.0]
 hand = torch.empty(N ** 3, device=dev); obj = torch.empty(N ** 3, device=dev)
-dbg = torch.zeros(32, dtype=torch.int64, device=dev)
+dbg = torch.zeros(512, dtype=torch.int64, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -30,9 +30,21 @@ e1.record()
 torch.cuda.synchronize()
 d = dbg.cpu().tolist()
 items = ((N ** 3 + 255) // 256 + 73) // 74 * 2
-print(f"N={N}  kernel {e0.elapsed_time(e1):.2f} ms  items/cluster ~{items}  (UMMA floor 33664 cyc/item)")
+print(f"flags={os.environ.get('ASDF_TC3_DEBUG_FLAGS', 0)} N={N}  kernel {e0.elapsed_time(e1):.2f} ms  items/cluster ~{items}  (UMMA floor 33664 cyc/item)")
 print(f"issuer: total {d[0] / items:.0f}/item | wait A {d[1] / items:.0f} | wait ring {d[2] / items:.0f} | wait acc-free {d[3] / items:.0f}")
 ph = d[8:24]
 for l in range(4):
     print(f"  layer {l}: epilogue waits for accumulator {ph[l] / items:8.0f}  hold-wait {ph[4 + l] / items:8.0f}  epilogue work {ph[8 + l] / items:8.0f}")
 print(f"  final: {ph[12] / items:.0f}")
+
+if not int(os.environ.get("ASDF_TC3_DEBUG_FLAGS", 0)) & 32:
+    sys.exit(0)
+import numpy as np
+fine = np.asarray(d[32:32 + 266], dtype=np.float64) / items
+ring, await_, accw = fine[:126].reshape(14, 9), fine[126:252].reshape(14, 9), fine[252:266]
+np.set_printoptions(linewidth=200, suppress=True, precision=0)
+print("issuer ring waits per N block (rows) x fill (P tile, chunk 0..7), cycles per item:")
+print(ring)
+print("issuer A waits per N block x fill:")
+print(await_)
+print("issuer accumulator-free waits per N block:", accw)
