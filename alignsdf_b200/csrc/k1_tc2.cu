@@ -112,16 +112,17 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b,
 // Lean forms used by the issuer: operands are the LOW descriptor words (address >> 4); the high
 // word (SBO = 1024 B, version 1, 128B swizzle) is the constant 0x40004040.  All operands are
 // warp-uniform so ptxas keeps them in uniform registers (no R2UR waterfall per UMMA).
-// `issue` != 0 only in the issuing lane: the instruction is predicated inside the asm, so the
-// surrounding code stays branch-free (no per-UMMA divergence handling).
+// The whole (converged) issuer warp executes these wrappers and elect.sync picks the issuing lane:
+// ptxas then emits the UTC*MMA directly (a `lane == 0` predicate made it wrap every UMMA in a
+// VOTEU / ELECT / BRA.U.ANY loop over the active lanes, ~50 cycles per UMMA; see k1_tc3.cu).
 __device__ __forceinline__ void umma_ss_lo(uint32_t issue, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
                "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
                "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
                :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void umma_ts_lo(uint32_t issue, uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
                "mov.b64 db, {%2, %5};\n\t"
                "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
                :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(0u), "r"(issue) : "memory");
@@ -130,14 +131,14 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t issue, uint32_t d, uint32_t 
 // halves 128 B apart (LBO), 8-row groups 256 B apart (SBO); B = SW128 tile as above.
 __device__ __forceinline__ void umma_ap(uint32_t issue, uint32_t d, uint32_t ap_addr, uint32_t b_lo, uint32_t acc) {
   const uint32_t a_lo = ((ap_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
-  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
                "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %5};\n\t"
                "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
                :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u),
                   "r"((256u >> 4) | (1u << 14)), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void umma_commit_both_if(uint32_t issue, uint32_t bar) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
                :: "r"(bar), "h"((uint16_t)3), "r"(issue) : "memory");
 }

@@ -42,7 +42,7 @@ NCU_TRAFFIC_BYTES = None   # filled from profiles/ by _ncu_traffic()
 
 def _ncu_traffic():
     """dram bytes (read + write) per 256^3 launch of the dominant kernel, from the committed ncu summary."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_tc2_eval_256.txt")
+    path = os.path.join(ROOT, "profiles", "r01_ncu_tc3_eval_256.txt")
     if not os.path.exists(path):
         return None
     tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -284,7 +284,7 @@ def main():
         line = dict(
             metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=value, unit="Mq/s",
             n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
-            scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f16x3 (fp32 accumulate)",
+            scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f16 main + 2 e4m3 correction products (fp32 accumulate)",
             data="synthetic", impl="b200",
             config=dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {N_SAMPLES} synthetic latents/poses",
                         decoder="SeparateDecoder 5x512, both/9", parallelism=f"zslab{world}" if world > 1 else "single",
@@ -296,12 +296,14 @@ def main():
         if world == 1 and k1_ms:
             k1 = sum(k1_ms) / len(k1_ms)
             ach = N ** 3 * F_MIN / (k1 * 1e-3) / 1e12
-            line["roofline"] = dict(bound="tensor", kernel="tc2_eval_kernel", achieved=ach, peak=peaks["tflops"],
+            # issued tensor work in fp16-MMA time: padded shapes x (1 fp16 product + 2 fp8 products at twice the rate)
+            issued = ach * 2 * (2 * 2 * 524288) / F_MIN
+            line["roofline"] = dict(bound="tensor", kernel="tc3_eval_kernel", achieved=ach, peak=peaks["tflops"],
                                     unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=NCU_TRAFFIC_BYTES,
                                     traffic_note="dram__bytes_read+write of one 256^3 launch, ncu --set full "
-                                                 "(profiles/r01_ncu_tc2_eval_256.txt); algorithmic HBM bytes = 8 B/query",
+                                                 "(profiles/r01_ncu_tc3_eval_256.txt); algorithmic HBM bytes = 8 B/query",
                                     ms_per_launch=k1, queries_per_launch=N ** 3, flop_per_query=F_MIN,
-                                    issued_tflops=ach * 3 * (2 * 2 * 524288) / F_MIN,
+                                    issued_tflops_f16_equiv=issued, fallbacks_to_fp16_kernel=engine.FALLBACKS["tc3_to_tc2"],
                                     frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
                                     Mq_per_s_kernel=N ** 3 / (k1 * 1e-3) / 1e6)
         if world == 1 and not args.no_cpu_baseline:
