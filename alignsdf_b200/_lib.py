@@ -92,6 +92,14 @@ def lib():
     L.asdf_mc_count.argtypes = [vp, C.POINTER(McParams), vp, vp, vp]
     L.asdf_mc_emit.restype = C.c_int
     L.asdf_mc_emit.argtypes = [vp, C.POINTER(McParams), vp, vp, vp, vp, vp, vp]
+    L.asdf_cc_label.restype = C.c_int
+    L.asdf_cc_label.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
+    L.asdf_cc_stats.restype = C.c_int
+    L.asdf_cc_stats.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, C.POINTER(C.c_float * 3), vp, vp, vp, vp, vp]
+    L.asdf_cc_mark.restype = C.c_int
+    L.asdf_cc_mark.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]
+    L.asdf_cc_gather.restype = C.c_int
+    L.asdf_cc_gather.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
     if L.asdf_abi_version() != 1:
         raise AsdfError("ABI version mismatch between alignsdf_b200 and its shared library")
     _lib = L

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libalignsdf_b200.so")
-SOURCES = ["api.cu", "k1_simt.cu", "k1_tc.cu", "k1_tc2.cu", "k1_tc3.cu", "mc.cu"]
+SOURCES = ["api.cu", "k1_simt.cu", "k1_tc.cu", "k1_tc2.cu", "k1_tc3.cu", "mc.cu", "cc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
 

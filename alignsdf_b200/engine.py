@@ -44,10 +44,24 @@ class BoundSample:
         self.engine = engine
         self.feature_mode = feature_mode
         self.device = engine.device
-        topo = engine.topo
-        pack = packer.pack_simt(branches)
+        self._simt_ready = False
+        self._two_outputs = len(branches) == 2 or int(branches[0].layers[-1].B.shape[0]) == 2
+        self.tc = None
+        self.tc2 = None
+        self.tc3 = None
+        self._branches = branches
+        if not feature_mode and engine.tc_supported:
+            from . import tc_pack
+            self.tc = tc_pack.bind(engine, branches)
+
+    def _ensure_simt(self):
+        """Buffers + descriptor of the generic fp32 kernel, built on first use (the tensor-core paths
+        never need them)."""
+        if self._simt_ready:
+            return
+        engine, topo, dev = self.engine, self.engine.topo, self.device
+        pack = packer.pack_simt(self._branches)
         self.simt_pack = pack
-        dev = self.device
         if engine.simt_static is None:      # static weights do not depend on the sample
             engine.simt_static = torch.from_numpy(pack.static).to(dev)
         self.simt_sample = torch.from_numpy(pack.sample).to(dev, non_blocking=True)
@@ -57,7 +71,7 @@ class BoundSample:
         d.n_class = 0 if topo.classifier is None else int(topo.classifier[0].shape[0])
         for b in range(pack.n_branches):
             d.point_dim[b] = int(pack.point_dim[b])
-            idx = (packer.branch_feature_index(topo, topo.branches[b][0]) if feature_mode
+            idx = (packer.branch_feature_index(topo, topo.branches[b][0]) if self.feature_mode
                    else np.arange(3))
             for k, v in enumerate(idx):
                 d.point_index[b][k] = int(v)
@@ -65,13 +79,7 @@ class BoundSample:
                 for k in range(6):
                     d.table[b][l][k] = int(pack.table[b, l, k])
         self.simt_desc = d
-        self.tc = None
-        self.tc2 = None
-        self.tc3 = None
-        self._branches = branches
-        if not feature_mode and engine.tc_supported:
-            from . import tc_pack
-            self.tc = tc_pack.bind(engine, branches)
+        self._simt_ready = True
 
     def _tc2_for(self, p_absmax: float):
         """Per-sample block of the v2 tensor-core kernel, valid for |xyz| <= p_absmax (the point
@@ -104,7 +112,7 @@ class BoundSample:
     def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str, p_absmax: float = 2.0):
         dev = self.device
         hand = torch.empty(n, dtype=torch.float32, device=dev)
-        two = self.simt_desc.n_branches == 2 or self.simt_desc.n_outputs == 2
+        two = self._two_outputs
         obj = torch.empty(n, dtype=torch.float32, device=dev) if two else None
         cls = torch.empty(n, dtype=torch.int32, device=dev) if want_cls else None
         box = None
@@ -161,6 +169,7 @@ class BoundSample:
                 _lib.check(rc, "asdf_tc_eval")
                 LAUNCHES["count"] += 1
             else:
+                self._ensure_simt()
                 rc = L.asdf_simt_eval(C.byref(self.simt_desc), _lib.ptr(self.engine.simt_static),
                                       _lib.ptr(self.simt_sample), _lib.ptr(self.engine.cls_dev),
                                       C.byref(q), _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(cls),
@@ -314,6 +323,75 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
                        "asdf_mc_emit")
             LAUNCHES["count"] += 1
     return dict(verts=verts, points=points, faces=faces, keys=keys)
+
+
+def ply_face_records(faces: torch.Tensor) -> torch.Tensor:
+    """Binary-PLY face records built on the device: uint8 [F,13] = list length 3 + the three int32
+    indices (little endian), ready to be written after the header and the vertex block."""
+    F = int(faces.shape[0])
+    rec = torch.empty((F, 13), dtype=torch.uint8, device=faces.device)
+    if F:
+        rec[:, 0] = 3
+        rec[:, 1:] = faces.contiguous().view(torch.uint8).view(F, 12)
+    return rec
+
+
+def select_component(points: torch.Tensor, faces: torch.Tensor, verts_local: torch.Tensor, dims, spacing):
+    """GPU version of trimesh_lite.largest_watertight_component_mc (utils/mesh.py:371-381): connected
+    components of a marching-cubes mesh, and -- iff at least two of them are watertight -- the
+    largest-area watertight one (first maximum in order of first face), compacted with vertex and
+    face order preserved.  points / verts_local: CUDA f32 [V,3], faces: CUDA int32 [F,3].
+    Returns (points, faces, info); the inputs themselves when the mesh is kept whole."""
+    _lib.require_cuda(points, "points")
+    V, F = int(points.shape[0]), int(faces.shape[0])
+    info = dict(components=0, watertight=0, kept="whole")
+    if F == 0 or V == 0:
+        return points, faces, info
+    L = _lib.lib()
+    dev = points.device
+    points = points.contiguous()
+    faces = faces.contiguous()
+    verts_local = verts_local.contiguous()
+    last = (C.c_float * 3)(*[float(np.float32(float(dims[k] - 1) * float(spacing[k]))) for k in range(3)])
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        parent = torch.empty(V, dtype=torch.int32, device=dev)
+        _lib.check(L.asdf_cc_label(_lib.ptr(faces), F, V, _lib.ptr(parent), st), "asdf_cc_label")
+        area = torch.zeros(V, dtype=torch.float64, device=dev)
+        acc = torch.zeros((2, V), dtype=torch.int32, device=dev)          # nfaces, open
+        first = torch.full((V,), INT_MAX, dtype=torch.int32, device=dev)
+        _lib.check(L.asdf_cc_stats(_lib.ptr(faces), F, _lib.ptr(verts_local), _lib.ptr(points), V, _lib.ptr(parent),
+                                   C.byref(last), _lib.ptr(area), _lib.ptr(acc[0]), _lib.ptr(acc[1]),
+                                   _lib.ptr(first), st), "asdf_cc_stats")
+        LAUNCHES["count"] += 4
+        roots = torch.nonzero(acc[0] > 0).flatten()
+        n = int(roots.shape[0])
+        info["components"] = n
+        if n <= 1:
+            return points, faces, info
+        small = torch.stack([area[roots], acc[0][roots].double(), acc[1][roots].double(), first[roots].double(),
+                             roots.double()]).cpu().numpy()
+        comp_area, nfaces, is_open, first_face, label = small
+        cand = np.nonzero((is_open == 0) & (nfaces >= 4))[0]
+        info["watertight"] = int(len(cand))
+        if len(cand) <= 1:
+            return points, faces, info
+        cand = cand[np.argsort(first_face[cand], kind="stable")]      # trimesh orders the pieces by first face
+        best = int(label[cand[int(np.argmax(comp_area[cand]))]])      # the reference keeps the first maximum
+        keep = torch.empty(V + F, dtype=torch.int32, device=dev)
+        _lib.check(L.asdf_cc_mark(_lib.ptr(parent), V, _lib.ptr(faces), F, best, _lib.ptr(keep[:V]), _lib.ptr(keep[V:]), st),
+                   "asdf_cc_mark")
+        scan_v = torch.cumsum(keep[:V], 0, dtype=torch.int32)
+        scan_f = torch.cumsum(keep[V:], 0, dtype=torch.int32)
+        nv, nf = int(scan_v[-1]), int(scan_f[-1])
+        out_p = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        out_f = torch.empty((nf, 3), dtype=torch.int32, device=dev)
+        _lib.check(L.asdf_cc_gather(_lib.ptr(points), _lib.ptr(faces), V, F, _lib.ptr(keep[:V]), _lib.ptr(scan_v),
+                                    _lib.ptr(keep[V:]), _lib.ptr(scan_f), _lib.ptr(out_p), _lib.ptr(out_f), st),
+                   "asdf_cc_gather")
+        LAUNCHES["count"] += 2
+    info["kept"] = best
+    return out_p, out_f, info
 
 
 def grid_points(N, voxel, origin, mode="reference", begin=0, end=None, device=None) -> torch.Tensor:

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
-from .trimesh_lite import Mesh, largest_watertight_component_mc, split as _split
+from .trimesh_lite import Mesh, export_ply_records, largest_watertight_component_mc, split as _split  # noqa: F401
 
 INT_MAX = 2 ** 31 - 1
 
@@ -103,16 +103,19 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
         print(e)
         res = (None, None, np.array([0, 0, 0]), np.array([1]))
         return res + (None,) if return_mesh else res
+    # trimesh.graph.split + "largest area piece if more than one" (:371-381) on the GPU (csrc/cc.cu); only the
+    # kept component and the raw marching-cubes arrays the reference returns travel to the host
+    sel_points, sel_faces, _ = _engine.select_component(out["points"], out["faces"], out["verts"], vol.shape, [vs] * 3)
+    ply_faces = _engine.ply_face_records(sel_faces).cpu().numpy()
+    mesh_points = sel_points.cpu().numpy()                 # origin + verts (f32), :360-363
     verts = out["verts"].cpu().numpy()
     faces = out["faces"].cpu().numpy()
-    mesh_points = out["points"].cpu().numpy()              # origin + verts (f32), :360-363
     if scale is not None:
         mesh_points = mesh_points * scale
     if offset is not None:
         mesh_points = mesh_points + offset
-    # trimesh.graph.split + "largest area piece if more than one" (:371-381), O(V+F) fast path
-    source_mesh = largest_watertight_component_mc(mesh_points, faces, verts, vol.shape, [vs] * 3)
-    source_mesh.export(ply_filename_out)
+    source_mesh = Mesh(mesh_points, faces if sel_faces is out["faces"] else sel_faces.cpu().numpy())
+    export_ply_records(ply_filename_out, mesh_points, ply_faces)
     res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
     return res + (source_mesh,) if return_mesh else res
 

@@ -64,6 +64,20 @@ def export_ply(path, vertices, faces):
         fh.write(rec.tobytes())
 
 
+def export_ply_records(path, vertices, face_records):
+    """Same file as export_ply, from face records already serialised on the GPU
+    (engine.ply_face_records: uint8 [F,13] = count byte 3 + three little-endian int32)."""
+    v = np.ascontiguousarray(vertices, dtype="<f4").reshape(-1, 3)
+    rec = np.ascontiguousarray(face_records, dtype=np.uint8).reshape(-1, 13)
+    header = ("ply\nformat binary_little_endian 1.0\n"
+              f"element vertex {len(v)}\nproperty float x\nproperty float y\nproperty float z\n"
+              f"element face {len(rec)}\nproperty list uchar int vertex_indices\nend_header\n")
+    with open(path, "wb") as fh:
+        fh.write(header.encode("ascii"))
+        fh.write(memoryview(v).cast("B"))
+        fh.write(memoryview(rec).cast("B"))
+
+
 def split(mesh: Mesh, only_watertight=True):
     """Connected components over faces sharing an edge, as sub-meshes (trimesh.graph.split)."""
     from scipy.sparse import coo_matrix

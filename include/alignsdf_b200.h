@@ -156,6 +156,25 @@ int asdf_mc_emit(const float* vol_dev, const asdf_mc_params* p, const void* scra
                  float* verts_dev, float* points_dev, int32_t* faces_dev, uint64_t* keys_dev,
                  void* stream);
 
+/* Connected components of a marching-cubes mesh and per-component statistics (K3).  Replaces
+ * trimesh.graph.split + the largest-area selection of utils/mesh.py:371-381.
+ * asdf_cc_label: parent_dev[V] <- smallest vertex index of the vertex's component (faces [F,3] int32).
+ * asdf_cc_stats: per-root accumulators (area_dev f64[V], nfaces_dev/open_dev i32[V] zeroed by the
+ *   caller, first_face_dev i32[V] initialised to INT_MAX): area on points_dev, number of faces,
+ *   open = some triangle edge lies in a boundary plane of the volume (verts_local_dev coordinate == 0
+ *   or == last_plane[k]), index of the component's first face.
+ * asdf_cc_mark / asdf_cc_gather: compaction of the component `best_label` around the caller's
+ *   inclusive prefix sums of keep_v / keep_f (vertex and face order are preserved). */
+int asdf_cc_label(const int32_t* faces_dev, int64_t F, int64_t V, int32_t* parent_dev, void* stream);
+int asdf_cc_stats(const int32_t* faces_dev, int64_t F, const float* verts_local_dev, const float* points_dev,
+                  int64_t V, const int32_t* parent_dev, const float last_plane[3], double* area_dev,
+                  int32_t* nfaces_dev, int32_t* open_dev, int32_t* first_face_dev, void* stream);
+int asdf_cc_mark(const int32_t* parent_dev, int64_t V, const int32_t* faces_dev, int64_t F, int32_t best_label,
+                 int32_t* keep_v_dev, int32_t* keep_f_dev, void* stream);
+int asdf_cc_gather(const float* points_dev, const int32_t* faces_dev, int64_t V, int64_t F,
+                   const int32_t* keep_v_dev, const int32_t* scan_v_dev, const int32_t* keep_f_dev,
+                   const int32_t* scan_f_dev, float* out_points_dev, int32_t* out_faces_dev, void* stream);
+
 int asdf_abi_version(void);
 const char* asdf_last_error(void);
 /* 1 if a CUDA device with compute capability 10.x is present, else 0 (never falls back). */

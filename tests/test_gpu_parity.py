@@ -300,3 +300,34 @@ def test_full_size_properties_128(dev):
         assert inv["nonmanifold_edges"] == 0 and inv["oriented"] and inv["closed"], (tag, inv)
         # every vertex lies within half a voxel of the iso-surface of the trilinear field
         assert out["faces"].shape[0] > 1000
+
+
+def test_gpu_component_selection_matches_host_split(dev):
+    """csrc/cc.cu (union-find labels, per-component area / open flag, compaction) == the generic
+    edge-adjacency split + largest-area selection of the oracle, on meshes with several closed
+    pieces, pieces cut by the volume boundary, a single piece and an empty mesh."""
+    from alignsdf_b200 import trimesh_lite
+    ax = np.linspace(-1, 1, 48, dtype=np.float32)
+    x, y, z = np.meshgrid(ax, ax, ax, indexing="ij")
+    sph = lambda c, r: np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) - np.float32(r)
+    sp = 2 / 47
+    cases = [np.minimum.reduce([sph((-0.4, 0, 0), 0.33), sph((0.5, 0.1, 0), 0.25), sph((0, 0.95, 0), 0.3),
+                                sph((0, -0.6, 0.6), 0.12), sph((0.6, 0.6, 0.6), 0.2)]),
+             sph((0, 0, 0), 0.5),
+             sph((0, 0.95, 0), 0.3),
+             np.minimum(sph((0.97, 0, 0), 0.3), sph((-0.3, 0, 0), 0.2)),
+             np.minimum(sph((-0.4, 0, 0), 0.3), sph((0.4, 0, 0), 0.3))]      # equal areas: the first piece wins
+    for vol in cases:
+        out = engine.marching_cubes(torch.from_numpy(vol).to(dev), 0.0, [sp] * 3, [-1.0, -1.0, -1.0])
+        p, f, info = engine.select_component(out["points"], out["faces"], out["verts"], vol.shape, [sp] * 3)
+        pts, faces, verts = out["points"].cpu().numpy(), out["faces"].cpu().numpy(), out["verts"].cpu().numpy()
+        ev, ef = mo.largest_component_if_split(pts, faces)
+        assert np.array_equal(p.cpu().numpy(), ev) and np.array_equal(f.cpu().numpy(), ef), info
+        m = trimesh_lite.largest_watertight_component_mc(pts, faces, verts, vol.shape, [sp] * 3)
+        assert np.array_equal(m.vertices, ev) and np.array_equal(m.faces, ef)
+        rec = engine.ply_face_records(f).cpu().numpy()
+        assert rec.shape == (len(ef), 13) and np.all(rec[:, 0] == 3)
+        assert np.array_equal(np.ascontiguousarray(rec[:, 1:]).view("<i4").reshape(-1, 3), ef)
+    empty = torch.empty((0, 3), device=dev)
+    p, f, info = engine.select_component(empty, torch.empty((0, 3), dtype=torch.int32, device=dev), empty, (4, 4, 4), [1.0] * 3)
+    assert p.shape[0] == 0 and f.shape[0] == 0 and info["kept"] == "whole"
