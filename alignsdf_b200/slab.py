@@ -217,15 +217,29 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     if rank != 0:
         return None
     result = {"hand": None, "obj": None}
+    from .trimesh_lite import Mesh, export_ply_records
+    vs = float(fields["voxel"])
     for tag in which:
-        verts, points, faces = (x.cpu().numpy() for x in meshes[tag])
-        if faces.shape[0] == 0:
+        verts_d, points_d, faces_d = meshes[tag]
+        if faces_d.shape[0] == 0:
             logging.warning("Cannot reconstruct mesh from '{}'".format(f"{filename}_{tag}.ply"))
             continue
-        if tag == "obj" and hand_branch:
-            points = points * np.array([1]) + np.array([0, 0, 0])      # utils/mesh.py:366-369, hand's values
-        m = largest_watertight_component_mc(points, faces, verts, (N, N, N), [float(fields["voxel"])] * 3)
-        if write:
-            m.export(f"{filename}_{tag}.ply")
+        if points_d.is_cuda:
+            # component filter + PLY face records on the GPU (csrc/cc.cu), like mesh.convert_sdf_samples_to_ply
+            sel_p, sel_f, _ = engine.select_component(points_d, faces_d, verts_d, (N, N, N), [vs] * 3)
+            rec = engine.ply_face_records(sel_f).cpu().numpy()
+            points = sel_p.cpu().numpy()
+            if tag == "obj" and hand_branch:
+                points = points * np.array([1]) + np.array([0, 0, 0])  # utils/mesh.py:366-369, hand's values
+            m = Mesh(points, sel_f.cpu().numpy())
+            if write:
+                export_ply_records(f"{filename}_{tag}.ply", points, rec)
+        else:                                   # host tensors (gloo tests with the oracle as backend)
+            verts, points, faces = (x.cpu().numpy() for x in meshes[tag])
+            if tag == "obj" and hand_branch:
+                points = points * np.array([1]) + np.array([0, 0, 0])
+            m = largest_watertight_component_mc(points, faces, verts, (N, N, N), [vs] * 3)
+            if write:
+                m.export(f"{filename}_{tag}.ply")
         result[tag] = m
     return result
