@@ -30,9 +30,10 @@ class Query(C.Structure):
 
 class SimtDesc(C.Structure):
     _fields_ = [("n_branches", C.c_int32), ("n_layers", C.c_int32), ("n_outputs", C.c_int32),
-                ("pre_tanh", C.c_int32), ("n_class", C.c_int32), ("point_dim", C.c_int32 * 2),
+                ("pre_tanh", C.c_int32), ("n_class", C.c_int32), ("nerf_freqs", C.c_int32),
+                ("point_dim", C.c_int32 * 2),
                 ("point_index", (C.c_int32 * ASDF_MAX_POINT_DIM) * 2),
-                ("table", ((C.c_int32 * 6) * ASDF_MAX_LAYERS) * 2)]
+                ("table", ((C.c_int32 * 8) * ASDF_MAX_LAYERS) * 2)]
 
 
 class TcDesc(C.Structure):
@@ -84,6 +85,8 @@ def lib():
     L.asdf_tc_sample_floats.restype = C.c_int64
     L.asdf_grid_points.restype = C.c_int
     L.asdf_grid_points.argtypes = [C.POINTER(Query), vp, vp]
+    L.asdf_nerf_embed.restype = C.c_int
+    L.asdf_nerf_embed.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     L.asdf_embed_points.restype = C.c_int
     L.asdf_embed_points.argtypes = [vp, C.c_int64, vp, C.c_int32, vp, vp]
     L.asdf_mc_scratch_bytes.restype = C.c_size_t

@@ -24,6 +24,13 @@ __global__ void embed_kernel(const float* __restrict__ xyz, int64_t P, const flo
   const float4 a = *reinterpret_cast<const float4*>(aff + 4 * f);
   feats[idx] = fmaf(a.x, x, fmaf(a.y, y, fmaf(a.z, z, a.w)));
 }
+// feats[p][f] for the public get_nerf_embedder() API
+__global__ void nerf_embed_kernel(const float* __restrict__ xyz, int64_t P, int pf, float* __restrict__ feats) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * pf) return;
+  const int64_t p = idx / pf;
+  feats[idx] = nerf_feature((int)(idx % pf), __ldg(xyz + p * 3), __ldg(xyz + p * 3 + 1), __ldg(xyz + p * 3 + 2));
+}
 __global__ void grid_points_kernel(asdf_query q, float* __restrict__ xyz) {
   const int64_t i = q.begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q.end) return;
@@ -34,6 +41,18 @@ __global__ void grid_points_kernel(asdf_query q, float* __restrict__ xyz) {
 }
 }  // namespace
 }  // namespace asdf
+
+extern "C" int asdf_nerf_embed(const float* xyz_dev, int64_t P, int32_t n_freqs, float* feats_dev, void* stream) {
+  using namespace asdf;
+  ASDF_REQUIRE(P >= 0 && n_freqs >= 0 && n_freqs <= 24, "asdf_nerf_embed: bad sizes");
+  if (P == 0) return ASDF_OK;
+  ASDF_REQUIRE(xyz_dev && feats_dev, "asdf_nerf_embed: null argument");
+  const int pf = 3 + 6 * n_freqs;
+  const int64_t n = P * pf;
+  nerf_embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz_dev, P, pf, feats_dev);
+  ASDF_CUDA_CHECK(cudaGetLastError());
+  return ASDF_OK;
+}
 
 extern "C" int asdf_grid_points(const asdf_query* q, float* xyz_dev, void* stream) {
   using namespace asdf;

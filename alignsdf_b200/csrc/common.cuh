@@ -51,6 +51,18 @@ __device__ __forceinline__ void grid_point(int64_t i, int N, int mode, float vox
   x2 = __fadd_rn(__fmul_rn(c2, voxel), o2);
 }
 
+// NeRF positional encoding of one coordinate triple (utils/utils.py:433-463): feature f of
+// [x(3), sin(x 2^0)(3), cos(x 2^0)(3), sin(x 2^1)(3), ...]; x * freq is a separate fp32 multiply like
+// torch's, sinf / cosf are the accurate (range-reducing) versions.
+__device__ __forceinline__ float nerf_feature(int f, float x0, float x1, float x2) {
+  const int a = f % 3;
+  const float x = a == 0 ? x0 : (a == 1 ? x1 : x2);
+  if (f < 3) return x;
+  const int g = (f - 3) / 3;                       // 0: sin 2^0, 1: cos 2^0, 2: sin 2^1, ...
+  const float arg = __fmul_rn(x, (float)(1 << (g >> 1)));
+  return (g & 1) ? cosf(arg) : sinf(arg);
+}
+
 // Warp-aggregated update of the 6-int bounding box of negative samples
 // (utils/mesh.py:207-247: nonzero(sdf<0) -> per-axis min/max over the *unravelled* index).
 __device__ __forceinline__ void bbox_update(int32_t* bbox, bool neg, int64_t i, int N) {

@@ -32,11 +32,12 @@ struct SimtArgs {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// out[n][p] = relu( sum_k WxT[k][n] in[k][p] + sum_d MB[n][d] u[d][p] + MB[n][D] )
+// out[n][p] = relu( sum_k WxT[k][n] in[k][p] + sum_d MB[n][d] u[d][p] + MB[n][D] )   (no relu when `raw`:
+// a LayerNorm follows)
 __device__ void hidden_layer(const float* __restrict__ wxt, const float* __restrict__ mb,
                              int h, int n, int npad, int has_m, int D,
                              const float* __restrict__ in, const float* __restrict__ u,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, bool raw) {
   const int tn = threadIdx.x & 63;
   const int p0 = (threadIdx.x >> 6) * 8;
   float acc[8][8];
@@ -79,11 +80,53 @@ __device__ void hidden_layer(const float* __restrict__ wxt, const float* __restr
   for (int j = 0; j < 8; ++j) {
     const int nn = tn + 64 * j;
     if (nn < n) {
-      float4 a = make_float4(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f), fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
-      float4 b = make_float4(fmaxf(acc[j][4], 0.f), fmaxf(acc[j][5], 0.f), fmaxf(acc[j][6], 0.f), fmaxf(acc[j][7], 0.f));
+      const float lo = raw ? -3.402823466e38f : 0.f;
+      float4 a = make_float4(fmaxf(acc[j][0], lo), fmaxf(acc[j][1], lo), fmaxf(acc[j][2], lo), fmaxf(acc[j][3], lo));
+      float4 b = make_float4(fmaxf(acc[j][4], lo), fmaxf(acc[j][5], lo), fmaxf(acc[j][6], lo), fmaxf(acc[j][7], lo));
       *reinterpret_cast<float4*>(out + nn * PTS + p0) = a;
       *reinterpret_cast<float4*>(out + nn * PTS + p0 + 4) = b;
     }
+  }
+}
+
+// x[k][p] <- relu(LayerNorm_k(x[.][p]) * gamma[k] + beta[k]) over the n features of every point of the
+// tile (nn.LayerNorm, eps 1e-5, biased variance, two-pass moments): one warp per 4 points.
+__device__ void layer_norm_relu(float* __restrict__ x, int n, const float* __restrict__ gamma,
+                                const float* __restrict__ beta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* col = x + warp * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < n; k += 32) {
+    const float4 v = ld4(col + k * PTS);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+  }
+  float mean[4], rstd[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+    mean[i] = s[i] / (float)n;
+    s[i] = 0.f;
+  }
+  for (int k = lane; k < n; k += 32) {
+    const float4 v = ld4(col + k * PTS);
+    const float d0 = v.x - mean[0], d1 = v.y - mean[1], d2 = v.z - mean[2], d3 = v.w - mean[3];
+    s[0] = fmaf(d0, d0, s[0]); s[1] = fmaf(d1, d1, s[1]); s[2] = fmaf(d2, d2, s[2]); s[3] = fmaf(d3, d3, s[3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+    rstd[i] = 1.0f / sqrtf(s[i] / (float)n + 1e-5f);
+  }
+  for (int k = lane; k < n; k += 32) {
+    const float g = __ldg(gamma + k), b = __ldg(beta + k);
+    float4 v = ld4(col + k * PTS);
+    v.x = fmaxf(fmaf((v.x - mean[0]) * rstd[0], g, b), 0.f);
+    v.y = fmaxf(fmaf((v.y - mean[1]) * rstd[1], g, b), 0.f);
+    v.z = fmaxf(fmaf((v.z - mean[2]) * rstd[2], g, b), 0.f);
+    v.w = fmaxf(fmaf((v.w - mean[3]) * rstd[3], g, b), 0.f);
+    *reinterpret_cast<float4*>(col + k * PTS) = v;
   }
 }
 
@@ -147,7 +190,16 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
         const int p = threadIdx.x;
         const int64_t i = base + p;
         if (i < q.end) {
-          if (q.mode == ASDF_QUERY_POINTS) {
+          if (d.nerf_freqs > 0) {                  // positional encoding of xyz, fused (never materialised)
+            float x0, x1, x2;
+            if (q.mode == ASDF_QUERY_POINTS) {
+              const float* row = q.points_dev + (size_t)i * q.point_stride;
+              x0 = __ldg(row); x1 = __ldg(row + 1); x2 = __ldg(row + 2);
+            } else {
+              grid_point(i, q.N, q.mode, q.voxel, q.origin[0], q.origin[1], q.origin[2], x0, x1, x2);
+            }
+            for (int dd = 0; dd < D; ++dd) u[dd * PTS + p] = nerf_feature(dd, x0, x1, x2);
+          } else if (q.mode == ASDF_QUERY_POINTS) {
             const float* row = q.points_dev + (size_t)i * q.point_stride;
             for (int dd = 0; dd < D; ++dd) u[dd * PTS + p] = __ldg(row + d.point_index[b][dd]);
           } else {
@@ -164,8 +216,12 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
       float* out = act1;
       for (int l = 0; l < L - 1; ++l) {
         const int32_t* t = d.table[b][l];
-        hidden_layer(a.stat + t[4], a.samp + t[5], t[0], t[1], t[2], t[3], D, in, u, out);
+        hidden_layer(a.stat + t[4], a.samp + t[5], t[0], t[1], t[2], t[3], D, in, u, out, t[6] >= 0);
         __syncthreads();
+        if (t[6] >= 0) {
+          layer_norm_relu(out, t[1], a.stat + t[6], a.stat + t[6] + t[1]);
+          __syncthreads();
+        }
         float* tmp = in; in = out; out = tmp;
       }
       const int32_t* t = d.table[b][L - 1];
@@ -237,6 +293,10 @@ extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_de
   ASDF_REQUIRE(desc->n_outputs >= 1 && desc->n_outputs <= 2, "n_outputs must be 1 or 2");
   ASDF_REQUIRE(desc->n_class >= 0 && desc->n_class <= 8, "n_class must be in [0,8]");
   ASDF_REQUIRE(desc->n_class == 0 || cls_dev, "classifier weights missing");
+  ASDF_REQUIRE(desc->nerf_freqs >= 0 && 3 + 6 * desc->nerf_freqs <= ASDF_MAX_POINT_DIM, "bad nerf_freqs");
+  if (desc->nerf_freqs > 0)
+    for (int b = 0; b < desc->n_branches; ++b)
+      ASDF_REQUIRE(desc->point_dim[b] == 3 + 6 * desc->nerf_freqs, "point_dim must be 3 + 6 nerf_freqs");
   ASDF_REQUIRE(q->end >= q->begin, "empty or negative query range");
   for (int b = 0; b < desc->n_branches; ++b) {
     ASDF_REQUIRE(desc->point_dim[b] >= 1 && desc->point_dim[b] <= ASDF_MAX_POINT_DIM, "bad point_dim");
@@ -249,12 +309,12 @@ extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_de
     ASDF_REQUIRE(desc->table[b][desc->n_layers - 1][1] == desc->n_outputs, "last layer width != n_outputs");
   }
   if (q->mode == ASDF_QUERY_POINTS) {
-    ASDF_REQUIRE(q->points_dev && q->point_stride >= 1, "points query without points");
+    ASDF_REQUIRE(q->points_dev && q->point_stride >= (desc->nerf_freqs > 0 ? 3 : 1), "points query without points");
   } else {
     ASDF_REQUIRE(q->mode == ASDF_QUERY_GRID_REFERENCE || q->mode == ASDF_QUERY_GRID_REGULAR, "bad query mode");
     ASDF_REQUIRE(q->N >= 2 && q->end <= (int64_t)q->N * q->N * q->N && q->begin >= 0, "grid range outside N^3");
-    ASDF_REQUIRE(desc->point_dim[0] == 3 && (desc->n_branches == 1 || desc->point_dim[1] == 3),
-                 "grid queries need xyz-folded weights (point_dim 3)");
+    ASDF_REQUIRE(desc->nerf_freqs > 0 || (desc->point_dim[0] == 3 && (desc->n_branches == 1 || desc->point_dim[1] == 3)),
+                 "grid queries need xyz-folded weights (point_dim 3) or the in-kernel NeRF encoding");
   }
   if (q->end == q->begin) return ASDF_OK;
   SimtArgs a;

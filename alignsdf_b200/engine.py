@@ -40,9 +40,10 @@ def _device_of(latent, device=None):
 class BoundSample:
     """A decoder with one sample's latent/pose folded in, ready to be queried."""
 
-    def __init__(self, engine, branches, feature_mode):
+    def __init__(self, engine, branches, feature_mode, nerf_freqs=0):
         self.engine = engine
         self.feature_mode = feature_mode
+        self.nerf_freqs = int(nerf_freqs)       # > 0: xyz queries, NeRF-encoded inside the generic kernel
         self.device = engine.device
         self._simt_ready = False
         self._two_outputs = len(branches) == 2 or int(branches[0].layers[-1].B.shape[0]) == 2
@@ -50,7 +51,7 @@ class BoundSample:
         self.tc2 = None
         self.tc3 = None
         self._branches = branches
-        if not feature_mode and engine.tc_supported:
+        if not feature_mode and not self.nerf_freqs and engine.tc_supported:
             from . import tc_pack
             self.tc = tc_pack.bind(engine, branches)
 
@@ -69,14 +70,15 @@ class BoundSample:
         d.n_branches, d.n_layers, d.n_outputs = pack.n_branches, pack.n_layers, pack.n_outputs
         d.pre_tanh = int(topo.pre_tanh)
         d.n_class = 0 if topo.classifier is None else int(topo.classifier[0].shape[0])
+        d.nerf_freqs = self.nerf_freqs
         for b in range(pack.n_branches):
             d.point_dim[b] = int(pack.point_dim[b])
-            idx = (packer.branch_feature_index(topo, topo.branches[b][0]) if self.feature_mode
+            idx = (packer.branch_feature_index(topo, topo.branches[b][0]) if self.feature_mode and not self.nerf_freqs
                    else np.arange(3))
             for k, v in enumerate(idx):
                 d.point_index[b][k] = int(v)
             for l in range(pack.n_layers):
-                for k in range(6):
+                for k in range(8):
                     d.table[b][l][k] = int(pack.table[b, l, k])
         self.simt_desc = d
         self._simt_ready = True
@@ -84,7 +86,7 @@ class BoundSample:
     def _tc2_for(self, p_absmax: float):
         """Per-sample block of the v2 tensor-core kernel, valid for |xyz| <= p_absmax (the point
         operand scale is baked into it); returns None when the fp16 ranges cannot be met."""
-        if self.feature_mode or not self.engine.tc_supported:
+        if self.feature_mode or self.nerf_freqs or not self.engine.tc_supported:
             return None
         need = max(2.0, float(p_absmax) * 1.01)
         if self.tc2 is None or self.tc2.info["p_absmax"] < need:
@@ -97,7 +99,7 @@ class BoundSample:
 
     def _tc3_for(self, p_absmax: float):
         """Same for the v3 kernel (its own block: activations are not pre-scaled there)."""
-        if self.feature_mode or not self.engine.tc_supported:
+        if self.feature_mode or self.nerf_freqs or not self.engine.tc_supported:
             return None
         need = max(2.0, float(p_absmax) * 1.01)
         if self.tc3 is None or self.tc3.info["p_absmax"] < need:
@@ -181,7 +183,7 @@ class BoundSample:
     def eval_grid(self, N, voxel, origin, mode="reference", begin=0, end=None, bbox_mask=0,
                   want_cls=False, path=None):
         """Evaluate linear grid indices [begin,end) -> (hand, obj, cls, bbox int32[12] or None)."""
-        if self.feature_mode:
+        if self.feature_mode and not self.nerf_freqs:
             raise AsdfError("grid evaluation needs an xyz-folded sample (feature_mode=False)")
         end = N ** 3 if end is None else end
         q = _lib.Query()
@@ -242,8 +244,12 @@ class DecoderEngine:
             self.tc_supported = False
 
     def bind(self, latent, specs, mano_results, obj_results, feature_mode=False) -> BoundSample:
-        branches = packer.fold_decoder(self.topo, latent, specs, mano_results, obj_results, feature_mode)
-        return BoundSample(self, branches, feature_mode)
+        # NeRF positional encoding (utils/mesh.py:54-55) is not affine in xyz: the weights are folded as
+        # for feature queries and the generic kernel encodes xyz itself
+        nerf = 0 if feature_mode else packer.nerf_freqs(specs, mano_results)
+        branches = packer.fold_decoder(self.topo, latent, specs, mano_results, obj_results,
+                                       feature_mode or nerf > 0)
+        return BoundSample(self, branches, feature_mode or nerf > 0, nerf)
 
 
 def unwrap_decoder(decoder):
@@ -408,6 +414,18 @@ def grid_points(N, voxel, origin, mode="reference", begin=0, end=None, device=No
         _lib.check(_lib.lib().asdf_grid_points(C.byref(q), _lib.ptr(out), _lib.stream_ptr(dev)),
                    "asdf_grid_points")
     return out
+
+
+def nerf_embed(xyz: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    """[..., 3] CUDA f32 -> [..., 3 + 6 n_freqs] NeRF positional encoding (utils/utils.py:521-533)."""
+    _lib.require_cuda(xyz, "xyz")
+    flat = xyz.to(torch.float32).reshape(-1, 3).contiguous()
+    out = torch.empty((flat.shape[0], 3 + 6 * int(n_freqs)), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().asdf_nerf_embed(_lib.ptr(flat), flat.shape[0], int(n_freqs), _lib.ptr(out),
+                                              _lib.stream_ptr(xyz.device)), "asdf_nerf_embed")
+    LAUNCHES["count"] += 1
+    return out.reshape(*xyz.shape[:-1], out.shape[-1])
 
 
 def embed_points(xyz: torch.Tensor, specs, mano_results, obj_results) -> torch.Tensor:

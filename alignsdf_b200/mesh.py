@@ -80,10 +80,12 @@ def _as_float_list(x):
 
 def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_size, ply_filename_out,
                                offset=None, scale=None, eval_mode=False, task='obman',
-                               return_mesh=False):
+                               return_mesh=False, raw_on_device=False):
     """Marching cubes (GPU) -> origin shift -> optional scale/offset -> largest watertight
     component if the mesh splits -> PLY.  Returns (verts, faces, trans, scale) like the reference
-    (raw marching-cubes vertices, i.e. before the origin shift and the component filter)."""
+    (raw marching-cubes vertices, i.e. before the origin shift and the component filter); with
+    ``raw_on_device`` those two stay CUDA tensors (create_mesh_combined_decoder only needs them on the
+    host for the label pass)."""
     if eval_mode:
         raise NotImplementedError("eval_mode (ICP against ground-truth meshes) is outside the hot "
                                   "path (SURVEY.md §2 #9)")
@@ -108,13 +110,18 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
     sel_points, sel_faces, _ = _engine.select_component(out["points"], out["faces"], out["verts"], vol.shape, [vs] * 3)
     ply_faces = _engine.ply_face_records(sel_faces).cpu().numpy()
     mesh_points = sel_points.cpu().numpy()                 # origin + verts (f32), :360-363
-    verts = out["verts"].cpu().numpy()
-    faces = out["faces"].cpu().numpy()
+    whole = sel_faces is out["faces"]
+    sel_faces_np = sel_faces.cpu().numpy()
+    if raw_on_device:
+        verts, faces = out["verts"], out["faces"]
+    else:
+        verts = out["verts"].cpu().numpy()
+        faces = sel_faces_np if whole else out["faces"].cpu().numpy()
     if scale is not None:
         mesh_points = mesh_points * scale
     if offset is not None:
         mesh_points = mesh_points + offset
-    source_mesh = Mesh(mesh_points, faces if sel_faces is out["faces"] else sel_faces.cpu().numpy())
+    source_mesh = Mesh(mesh_points, sel_faces_np)
     export_ply_records(ply_filename_out, mesh_points, ply_faces)
     res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
     return res + (source_mesh,) if return_mesh else res
@@ -175,11 +182,11 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
     if hand_branch:
         vertices, mesh_faces, offset, scale, mesh = convert_sdf_samples_to_ply(
             vols["hand"], voxel_origin, voxel_size, ply_filename_hand + ".ply", None, None, eval_mode,
-            task, return_mesh=True)
+            task, return_mesh=True, raw_on_device=True)
         result["hand"] = mesh
         if label_out and (vertices is not None):
             # utils/mesh.py:137-184: re-query the decoder at the marching-cubes vertices
-            v = torch.from_numpy(vertices).clone()
+            v = vertices.cpu().clone()
             for k in range(3):
                 v[:, k] = voxel_origin[k] + v[:, k]
             bound = vols["bound"]
@@ -195,6 +202,6 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
         # the object mesh reuses the HAND call's offset/scale (utils/mesh.py:186-194)
         *_, mesh = convert_sdf_samples_to_ply(vols["obj"], voxel_origin, voxel_size,
                                               ply_filename_obj + ".ply", offset, scale, False,
-                                              return_mesh=True)
+                                              return_mesh=True, raw_on_device=True)
         result["obj"] = mesh
     return result

@@ -66,23 +66,25 @@ class Topology:
     branches: list            # [(tag, prefix)]
     n_layers: int             # linear layers per branch
     layers: dict = field(default_factory=dict)      # prefix -> [(W, b)]
+    layer_norms: dict = field(default_factory=dict) # prefix -> [None | (gamma, beta)]  (LayerNorm before the ReLU)
     classifier: tuple | None = None                 # (Wc, bc)
 
 
 def decoder_topology(decoder) -> Topology:
     sd = _clean_state_dict(decoder)
-    if any(k.startswith("bn") for k in sd):
-        raise NotImplementedError("LayerNorm decoders (weight_norm=False with norm_layers) "
-                                  "are a 'next' row (SURVEY.md §8f); not built yet")
     separate = any(k.startswith("linh") for k in sd)
     prefixes = [("hand", "linh"), ("obj", "lino")] if separate else [("both", "lin")]
-    layers = {}
+    layers, layer_norms = {}, {}
     for _, prefix in prefixes:
-        ls, i = [], 0
+        ls, lns, i = [], [], 0
+        bn = prefix.replace("lin", "bn")                  # bnh / bno / bn: nn.LayerNorm when weight_norm is off
         while any(k.startswith(f"{prefix}{i}.") for k in sd):
             ls.append((_layer_weight(sd, f"{prefix}{i}"), sd[f"{prefix}{i}.bias"]))
+            lns.append((sd[f"{bn}{i}.weight"], sd[f"{bn}{i}.bias"]) if f"{bn}{i}.weight" in sd else None)
             i += 1
-        layers[prefix] = ls
+        if lns and lns[-1] is not None:
+            raise ValueError("LayerNorm on the output layer is not something the reference can build")
+        layers[prefix], layer_norms[prefix] = ls, lns
     n_layers = len(next(iter(layers.values())))
     if n_layers < 2 or n_layers > ASDF_MAX_LAYERS:
         raise ValueError(f"unsupported number of linear layers: {n_layers}")
@@ -103,7 +105,7 @@ def decoder_topology(decoder) -> Topology:
         latent_in=tuple(int(x) for x in getattr(decoder, "latent_in", ())),
         xyz_in_all=bool(getattr(decoder, "xyz_in_all", False)),
         pre_tanh=bool(getattr(decoder, "use_tanh", False)),
-        branches=prefixes, n_layers=n_layers, layers=layers, classifier=cls)
+        branches=prefixes, n_layers=n_layers, layers=layers, layer_norms=layer_norms, classifier=cls)
 
 
 # ----------------------------------------------------------------------------
@@ -113,6 +115,17 @@ def uses_kinematic_embedding(specs, mano_results) -> bool:
     """Condition at utils/mesh.py:49-50."""
     return (specs["PointFeatSize"] > 3 and mano_results is not None
             and specs["EncodeStyle"] != "nerf")
+
+
+def nerf_freqs(specs, mano_results) -> int:
+    """Number of NeRF frequencies when the reference takes the positional-encoding branch
+    (utils/mesh.py:49-55: PointFeatSize > 3 and (no MANO results or EncodeStyle 'nerf')), else 0."""
+    pf = int(specs["PointFeatSize"])
+    if pf <= 3 or uses_kinematic_embedding(specs, mano_results):
+        return 0
+    if (pf - 3) % 6 != 0:
+        raise ValueError(f"PointFeatSize={pf} is not 3 + 6 * multires (NeRF positional encoding)")
+    return (pf - 3) // 6
 
 
 def _rigid_inverse(T: np.ndarray, what: str):
@@ -128,8 +141,8 @@ def embedding_affine(specs, mano_results, obj_results):
     pf = int(specs["PointFeatSize"])
     if not uses_kinematic_embedding(specs, mano_results):
         if pf != 3:
-            raise NotImplementedError("NeRF positional encoding (PointFeatSize>3 without a "
-                                      "kinematic embedding) is a 'next' row (SURVEY.md §8f)")
+            raise ValueError("NeRF positional encoding is not an affine map of xyz: fold with "
+                             "feature_mode=True and let the kernel encode (packer.nerf_freqs)")
         return np.eye(3), np.zeros(3)
     style = specs["EncodeStyle"]
     s = float(specs["SdfScaleFactor"])
@@ -190,6 +203,7 @@ class FoldedLayer:
     Wx: np.ndarray | None     # [out, h] f32, weights on the previous activations
     M: np.ndarray | None      # [out, D] f32, weights on the per-point vector u
     B: np.ndarray             # [out]    f32
+    ln: tuple | None = None   # (gamma [out], beta [out]) f32: LayerNorm(eps 1e-5) between the linear map and the ReLU
 
 
 @dataclass
@@ -241,6 +255,10 @@ def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
             else:
                 folded.append(FoldedLayer(W, None, b.copy()))
         D = A.shape[1]
+        for l, fl in enumerate(folded):
+            ln = topo.layer_norms.get(prefix, [None] * len(folded))[l]
+            fl.ln = None if ln is None else (np.ascontiguousarray(ln[0], dtype=np.float32),
+                                             np.ascontiguousarray(ln[1], dtype=np.float32))
         for fl in folded:
             fl.Wx = None if fl.Wx is None else np.ascontiguousarray(fl.Wx, dtype=np.float32)
             fl.M = None if fl.M is None else np.ascontiguousarray(fl.M, dtype=np.float32)
@@ -266,6 +284,10 @@ def folded_forward_numpy(branches, u: np.ndarray, pre_tanh=False, dtype=np.float
                     y = np.tanh(y)
                 y = np.tanh(y)
             else:
+                if fl.ln is not None:
+                    mu = y.mean(1, keepdims=True)
+                    var = ((y - mu) ** 2).mean(1, keepdims=True)
+                    y = (y - mu) / np.sqrt(var + dtype(1e-5)) * fl.ln[0].astype(dtype) + fl.ln[1].astype(dtype)
                 y = np.maximum(y, 0)
             x = y
         res.append(x)
@@ -283,9 +305,10 @@ def _pad8(n):
 class SimtPack:
     """Flat float buffers + an int32 table in the layout k1_simt.cu reads.
 
-    static  : per branch, per layer  WxT [h][npad]   (transposed, zero padded)
+    static  : per branch, per layer  WxT [h][npad]   (transposed, zero padded), then gamma [n] | beta [n]
+              when the layer is followed by a LayerNorm
     sample  : per branch, per layer  MB  [npad][D+1] (M row then B)
-    table   : per branch, per layer  (h, n, npad, has_M, off_static, off_sample)
+    table   : per branch, per layer  (h, n, npad, has_M, off_static, off_sample, off_layernorm or -1, 0)
     """
     static: np.ndarray
     sample: np.ndarray
@@ -320,13 +343,22 @@ def pack_simt(branches) -> SimtPack:
                 mb[:n, :D] = fl.M
             mb[:n, D] = fl.B
             sample.append(mb.reshape(-1))
-            table.append((h, n, npad, int(fl.M is not None), off_s, off_p))
+            off_ln = -1
+            off_w = off_s
             off_s += h * npad
+            if fl.ln is not None:
+                static.append(np.concatenate([fl.ln[0], fl.ln[1]]).astype(np.float32))
+                off_ln = off_s
+                off_s += 2 * n
+                if off_s % 4:                           # keep the next weight block 16-byte aligned
+                    static.append(np.zeros(4 - off_s % 4, np.float32))
+                    off_s += 4 - off_s % 4
+            table.append((h, n, npad, int(fl.M is not None), off_w, off_p, off_ln, 0))
             off_p += npad * (D + 1)
     return SimtPack(
         static=np.concatenate(static) if static else np.zeros(1, np.float32),
         sample=np.concatenate(sample),
-        table=np.asarray(table, np.int32).reshape(len(branches), n_layers, 6),
+        table=np.asarray(table, np.int32).reshape(len(branches), n_layers, 8),
         n_branches=len(branches), n_layers=n_layers,
         point_dim=np.asarray([b.point_dim for b in branches], np.int32),
         n_outputs=int(branches[0].layers[-1].B.shape[0]), max_width=int(max_w))

@@ -122,10 +122,41 @@ def make_decoder(seed: int, kind="separate", latent_size=256, point_feat_size=9,
         torch.manual_seed(0)  # nn.Linear default init is overwritten below anyway
         dec = cls(latent_size, point_feat_size, encode_style, use_classifier=use_classifier, **ns)
     g = _gen(7_000_001 * (seed + 1))
+    has_ln = False
     for name, mod in dec.named_children():  # registration order == deterministic
         if hasattr(mod, "weight_v") or isinstance(mod, torch.nn.Linear):
             _fill_linear(g, mod, 1.0)
+        elif isinstance(mod, torch.nn.LayerNorm):
+            has_ln = True
+            with torch.no_grad():
+                mod.weight.copy_((1.0 + 0.2 * _gauss(g, *mod.weight.shape)).float())
+                mod.bias.copy_((0.1 * _gauss(g, *mod.bias.shape)).float())
+    if has_ln:
+        return _center_outputs(dec, seed, latent_size, point_feat_size, encode_style).eval()
     return _engineer(dec, seed).eval()
+
+
+def _center_outputs(dec, seed, latent_size, point_feat_size, encode_style, frac_negative=0.3):
+    """LayerNorm decoders: the ellipsoid wiring of _engineer does not survive the normalisation, so the
+    last-layer biases are shifted until ``frac_negative`` of a coarse grid (for the sample of the same
+    seed) is inside -- a zero level set exists and the bbox re-grid is exercised."""
+    from . import packer
+    sample = make_sample(seed, latent_size, point_feat_size, encode_style)
+    ax = torch.linspace(-1, 1, 9)
+    xyz = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    feats = packer.embed_points_torch(xyz, sample) if packer.uses_kinematic_embedding(sample.specs, sample.mano_results) else xyz
+    x = torch.cat([sample.latent.expand(xyz.shape[0], -1), feats], 1)
+    dec.eval()
+    with torch.no_grad():
+        out = dec(x)
+        sep = isinstance(dec, SeparateDecoder)
+        n_lin = (dec.num_hand_layers if sep else dec.num_layers) - 1
+        for o, prefix in enumerate(("linh", "lino") if sep else ("lin", "lin")):
+            pre = torch.atanh(out[o][:, 0].double().clamp(-0.999999, 0.999999))
+            shift = torch.quantile(pre, frac_negative)
+            last = getattr(dec, f"{prefix}{n_lin - 1}")
+            last.bias[o if not sep else 0] -= shift.float()
+    return dec
 
 
 # ----------------------------------------------------------------------------

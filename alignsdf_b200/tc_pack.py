@@ -35,6 +35,8 @@ def supported(topo) -> bool:
         return False
     if tuple(topo.latent_in) != (2,):
         return False
+    if any(ln is not None for lns in topo.layer_norms.values() for ln in lns):
+        return False                      # LayerNorm decoders run on the generic kernel
     for _, prefix in topo.branches:
         ls = topo.layers[prefix]
         d0 = ls[0][0].shape[1]

@@ -1,6 +1,7 @@
 """Drop-in for the hot-path part of the reference's ``utils/utils.py``.
 
     kinematic_embedding      <-> utils/utils.py:376-430
+    get_nerf_embedder        <-> utils/utils.py:521-533
     decode_sdf_multi_output  <-> utils/utils.py:561-572
     decode_sdf_points        (new) the fast arbitrary-point path: raw xyz in, pose-align folded
 
@@ -25,6 +26,12 @@ def kinematic_embedding(xyz, mano_results, num_points_per_scene, point_feat_size
     if point_feat_size <= 3:
         raise ValueError("kinematic_embedding needs PointFeatSize > 3")
     return _engine.embed_points(xyz, specs, mano_results, obj_results)
+
+
+def get_nerf_embedder(multires):
+    """-> (embed, out_dim) like the reference: embed(x[..., 3]) = [x, sin(2^f x), cos(2^f x) ...]."""
+    multires = int(multires)
+    return (lambda x, m=multires: _engine.nerf_embed(x, m)), 3 + 6 * multires
 
 
 def decode_sdf_multi_output(decoder, latent_vector, queries, mano_results, cam_intr, specs):

@@ -59,12 +59,17 @@ typedef struct {
   int32_t n_outputs;                        /* width of the last layer (1 or 2) */
   int32_t pre_tanh;                         /* NetworkSpecs.use_tanh */
   int32_t n_class;                          /* classifier logits on the penultimate activations, 0 = none */
+  int32_t nerf_freqs;                       /* > 0: u = NeRF positional encoding of the query's xyz, computed in the
+                                               kernel: [x, sin(2^f x), cos(2^f x)] for f < nerf_freqs (utils/utils.py:
+                                               433-463,521-533; utils/mesh.py:54-55); point_dim must be 3 + 6 nerf_freqs */
   int32_t point_dim[2];                     /* D per branch: 3 (xyz) or the branch's feature count */
   int32_t point_index[2][ASDF_MAX_POINT_DIM]; /* column of the query row feeding u[d] */
-  int32_t table[2][ASDF_MAX_LAYERS][6];     /* h, n, npad, has_M, off_static, off_sample (in floats) */
+  int32_t table[2][ASDF_MAX_LAYERS][8];     /* h, n, npad, has_M, off_static, off_sample (in floats),
+                                               off_layernorm (gamma[n] | beta[n] in static_dev, -1 = none), 0 */
 } asdf_simt_desc;
 
-/* y_l = relu(WxT_l^T x + M_l u + B_l) ... tanh;   static_dev: WxT blocks, sample_dev: [npad][D+1] blocks,
+/* y_l = relu(LN_l(WxT_l^T x + M_l u + B_l)) ... tanh  (LN_l = LayerNorm, eps 1e-5, only where off_layernorm >= 0:
+ * networks/model.py:254-255,317-319);   static_dev: WxT blocks, sample_dev: [npad][D+1] blocks,
  * cls_dev: [n_class][h_last+1] (weights then bias) or NULL.
  * out_hand_dev / out_obj_dev: [end-begin] f32.  out_cls_dev: [end-begin] int32 argmax or NULL.
  * bbox_dev: int32[12] = hand {min0,min1,min2,max0,max1,max2} then object {...}, updated with
@@ -127,6 +132,10 @@ int64_t asdf_tc_sample_floats(void);
 /* Query coordinates only (tests / debugging): xyz_dev [end-begin,3], bit-exact w.r.t. the
  * reference's torch expressions at utils/mesh.py:32-40,86-94. */
 int asdf_grid_points(const asdf_query* q, float* xyz_dev, void* stream);
+
+/* NeRF positional encoding for the public get_nerf_embedder() API (utils/utils.py:521-533):
+ * feats[P, 3 + 6 n_freqs] = [x, sin(x 2^0), cos(x 2^0), sin(x 2^1), ...]. */
+int asdf_nerf_embed(const float* xyz_dev, int64_t P, int32_t n_freqs, float* feats_dev, void* stream);
 
 /* Pose-align embedding as an affine map: feats[P,pf] = xyz[P,3] A^T + c.
  * Replaces utils/utils.py:376-430 for the public kinematic_embedding() API. */

@@ -95,13 +95,25 @@ def kinematic_embedding(xyz, mano_results, point_feat_size, scale_factor, obj_re
     return out
 
 
+def nerf_embedding(xyz, multires):
+    """utils/utils.py:433-463,521-533 (Embedder / get_nerf_embedder): [x, sin(x f), cos(x f) for
+    f = 2^0 .. 2^(multires-1)] along the last axis, fp32; the frequencies come from
+    2.**torch.linspace(0, multires-1, multires) like the reference's."""
+    freq_bands = 2. ** torch.linspace(0., multires - 1, steps=multires)
+    out = [xyz]
+    for freq in freq_bands:
+        out.append(torch.sin(xyz * freq))
+        out.append(torch.cos(xyz * freq))
+    return torch.cat(out, -1)
+
+
 def embed(xyz, specs, mano_results, obj_results):
     """Feature selection logic of utils/mesh.py:49-55."""
     if specs["PointFeatSize"] > 3:
         if mano_results is not None and specs["EncodeStyle"] != "nerf":
             return kinematic_embedding(xyz, mano_results, specs["PointFeatSize"],
                                        specs["SdfScaleFactor"], obj_results, specs["EncodeStyle"])
-        raise NotImplementedError("NeRF positional encoding is out of the oracle's scope")
+        return nerf_embedding(xyz, (specs["PointFeatSize"] - 3) // 6)      # utils/mesh.py:54-55
     return xyz
 
 
@@ -132,6 +144,9 @@ def _mlp(sd, prefix, x, latent_in, pre_tanh, xyz_all=None):
         if l == n - 1 and pre_tanh:
             x = torch.tanh(x)
         if l < n - 1:
+            bn = prefix.replace("lin", "bn") + str(l)                # :254-255,317-319 LayerNorm (weight_norm off)
+            if f"{bn}.weight" in sd:
+                x = torch.nn.functional.layer_norm(x, (x.shape[1],), sd[f"{bn}.weight"], sd[f"{bn}.bias"], 1e-5)
             x = torch.relu(x)
     return torch.tanh(x), cls_in                                     # :324-325 final tanh
 

@@ -60,6 +60,12 @@ CASES = [
          xyz_in_all=True),
     dict(name="sep_both9_n20_objonly", kind="separate", pf=9, style="both", N=20, seed=9,
          hand_branch=False),
+    # NeRF positional encoding of xyz (utils/mesh.py:54-55): pf = 3 + 6 * multires
+    dict(name="sep_nerf27_n12", kind="separate", pf=27, style="nerf", N=12, seed=11),
+    dict(name="comb_nerf15_n12", kind="combined", pf=15, style="nerf", N=12, seed=12),
+    # LayerNorm instead of weight norm (NetworkSpecs.weight_norm = false, networks/model.py:254-255,317-319)
+    dict(name="sep_ln_both9_n12", kind="separate", pf=9, style="both", N=12, seed=13, weight_norm=False),
+    dict(name="comb_ln_both9_n12", kind="combined", pf=9, style="both", N=12, seed=14, weight_norm=False),
 ]
 
 
@@ -96,6 +102,8 @@ def run_reference_case(case):
     ns = dict(synthetic.NETWORK_SPECS)
     if case.get("xyz_in_all"):
         ns["xyz_in_all"] = True
+    if case.get("weight_norm") is False:
+        ns["weight_norm"] = False
     use_cls = bool(case.get("use_classifier", False))
     mine = synthetic.make_decoder(seed, kind, 256, pf, style, ns, use_classifier=use_cls)
     sample = synthetic.make_sample(seed, 256, pf, style)
@@ -113,6 +121,7 @@ def run_reference_case(case):
     orig_cube = ref_mesh.get_higher_res_cube
     orig_decode = ref_mesh.decode_sdf_multi_output
     orig_embed = ref_mesh.kinematic_embedding
+    orig_nerf = ref_mesh.get_nerf_embedder
 
     def cube_wrap(hb, ob, vh, vo, n, origin, vs):
         nv, no = orig_cube(hb, ob, vh, vo, n, origin, vs)
@@ -135,6 +144,15 @@ def run_reference_case(case):
     ref_mesh.get_higher_res_cube = cube_wrap
     ref_mesh.decode_sdf_multi_output = decode_wrap
     ref_mesh.kinematic_embedding = embed_wrap
+
+    def nerf_wrap(multires):
+        fn, dim = orig_nerf(multires)
+
+        def fn2(x):
+            cap.xyz.append(x.clone().numpy())
+            return fn(x)
+        return fn2, dim
+    ref_mesh.get_nerf_embedder = nerf_wrap
     hb, ob = case.get("hand_branch", True), case.get("obj_branch", True)
     try:
         with tempfile.TemporaryDirectory() as td, torch.no_grad():
@@ -146,6 +164,7 @@ def run_reference_case(case):
         ref_mesh.get_higher_res_cube = orig_cube
         ref_mesh.decode_sdf_multi_output = orig_decode
         ref_mesh.kinematic_embedding = orig_embed
+        ref_mesh.get_nerf_embedder = orig_nerf
 
     # pass-2 volumes arrive via the MC hook (hand first if requested, then obj)
     vols = {}
@@ -178,7 +197,8 @@ def run_reference_case(case):
     if ob:
         errs["p1o"] = float(np.abs(res["pass1_obj"].numpy() - p1o).max())
         errs["p2o"] = float(np.abs(res["obj"].numpy() - vols["obj"]).max())
-    assert max(errs.values()) <= 1e-6, errs
+    # LayerNorm decoders amplify fp32 summation-order noise (outputs span the whole tanh range): 2e-6 there
+    assert max(errs.values()) <= (2e-6 if case.get("weight_norm") is False else 1e-6), errs
     cls = None
     if cap.logits:
         lg = np.concatenate(cap.logits, 0)

@@ -331,3 +331,15 @@ def test_gpu_component_selection_matches_host_split(dev):
     empty = torch.empty((0, 3), device=dev)
     p, f, info = engine.select_component(empty, torch.empty((0, 3), dtype=torch.int32, device=dev), empty, (4, 4, 4), [1.0] * 3)
     assert p.shape[0] == 0 and f.shape[0] == 0 and info["kept"] == "whole"
+
+
+def test_nerf_embedder_api_matches_oracle(dev):
+    """utils.get_nerf_embedder (utils/utils.py:521-533) on the GPU vs the oracle's torch-CPU restatement."""
+    xyz = torch.rand(4, 333, 3, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    for multires in (1, 4, 10):
+        embed, dim = autils.get_nerf_embedder(multires)
+        got = embed(xyz.to(dev))
+        want = orc.nerf_embedding(xyz, multires)
+        assert dim == 3 + 6 * multires and tuple(got.shape) == (4, 333, dim)
+        assert torch.equal(got[..., :3].cpu(), xyz)
+        assert (got.cpu() - want).abs().max() <= 2e-6      # sinf/cosf of arguments up to 2^9: a few ulp
