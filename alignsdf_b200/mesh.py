@@ -139,14 +139,15 @@ def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_fi
 
 
 def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
-                obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None):
+                obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None, bound=None):
     """The two evaluation passes of utils/mesh.py:24-120 on the GPU.
 
     Returns dict(pass1_hand, pass1_obj, hand, obj, cls, voxel (0-dim f32 tensor),
     origin (f32[3] tensor), bound) with [N,N,N] CUDA volumes."""
     dev = _engine._device_of(latent_vec, device)
     eng = _engine.get_engine(decoder, dev)
-    bound = eng.bind(latent_vec, specs, mano_results, obj_results)
+    if bound is None:                    # ``bound``: a sample already bound by the caller (pipelined batches)
+        bound = eng.bind(latent_vec, specs, mano_results, obj_results)
     voxel_size = 2.0 / (N - 1)
     mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
     if mask == 0:
@@ -205,3 +206,93 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
                                               return_mesh=True, raw_on_device=True)
         result["obj"] = mesh
     return result
+
+
+def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True, obj_branch=True,
+                            grid_mode="reference", device=None):
+    """Batch form of ``create_mesh_combined_decoder`` for loops like reconstruct.py:70-93 (one call per test
+    image): the two grid passes of sample i+1 run while a worker thread extracts, filters, reads back and
+    writes the meshes of sample i on a second CUDA stream, so the host-side stages no longer leave the GPU
+    idle between samples.  ``samples``: iterable of objects with ``latent``, ``mano_results``,
+    ``obj_results``, ``specs`` (host or CUDA tensors); ``filenames``: output prefixes.  Same files and
+    meshes as the one-call-per-sample loop; returns the list of ``{"hand": mesh, "obj": mesh}`` dicts."""
+    import queue
+    import threading
+    decoder.eval()
+    results, errors = {}, []
+    work = queue.Queue(maxsize=2)                      # at most two samples' volumes alive
+
+    def finish():
+        stream = None
+        while True:
+            item = work.get()
+            if item is None:
+                return
+            idx, vols, done, prefix = item
+            try:
+                dev = vols["hand"].device
+                if stream is None:
+                    stream = torch.cuda.Stream(dev)
+                with torch.cuda.device(dev), torch.cuda.stream(stream):
+                    stream.wait_event(done)
+                    out = {"hand": None, "obj": None}
+                    voxel_origin = vols["origin"].tolist()
+                    offset = scale = None
+                    if hand_branch:
+                        _, _, offset, scale, out["hand"] = convert_sdf_samples_to_ply(
+                            vols["hand"], voxel_origin, vols["voxel"], prefix + "_hand.ply", None, None, False,
+                            return_mesh=True, raw_on_device=True)
+                    if obj_branch:
+                        *_, out["obj"] = convert_sdf_samples_to_ply(
+                            vols["obj"], voxel_origin, vols["voxel"], prefix + "_obj.ply", offset, scale, False,
+                            return_mesh=True, raw_on_device=True)
+                results[idx] = out
+            except Exception as e:                     # surfaced on the caller's thread
+                errors.append(e)
+                results[idx] = None
+
+    worker = threading.Thread(target=finish, daemon=True)
+    worker.start()
+    from concurrent.futures import ThreadPoolExecutor
+    samples, filenames = list(samples), list(filenames)
+    bind_stream = {}
+
+    def bind(i):
+        """Fold + pack + upload sample i (host work ~3 ms) on its own stream, ahead of its turn."""
+        smp = samples[i]
+        dev = _engine._device_of(smp.latent, device)
+        if dev not in bind_stream:
+            bind_stream[dev] = torch.cuda.Stream(dev)
+        with torch.cuda.device(dev), torch.cuda.stream(bind_stream[dev]):
+            to = lambda t: t.to(dev, non_blocking=True)
+            latent = to(smp.latent)
+            mano = None if smp.mano_results is None else {k: to(v) for k, v in smp.mano_results.items()}
+            obj = None if smp.obj_results is None else {k: to(v) for k, v in smp.obj_results.items()}
+            bound = _engine.get_engine(decoder, dev).bind(latent, smp.specs, mano, obj)
+            bound._tc3_for(2.0)                      # pre-pack the tensor-core block for the unit cube
+            ready = torch.cuda.Event()
+            ready.record(bind_stream[dev])
+        return dev, latent, mano, obj, bound, ready
+
+    n = 0
+    try:
+        with ThreadPoolExecutor(max_workers=1) as binder:
+            nxt = binder.submit(bind, 0) if samples else None
+            for idx, prefix in enumerate(filenames[:len(samples)]):
+                if errors:
+                    break
+                dev, latent, mano, obj, bound, ready = nxt.result()
+                nxt = binder.submit(bind, idx + 1) if idx + 1 < len(samples) else None
+                torch.cuda.current_stream(dev).wait_event(ready)
+                vols = sdf_volumes(decoder, latent, mano, obj, samples[idx].specs, N, hand_branch, obj_branch,
+                                   False, dev, grid_mode, bound=bound)
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                work.put((idx, vols, done, prefix))
+                n += 1
+    finally:
+        work.put(None)
+        worker.join()
+    if errors:
+        raise errors[0]
+    return [results[i] for i in range(n)]

@@ -343,3 +343,26 @@ def test_nerf_embedder_api_matches_oracle(dev):
         assert dim == 3 + 6 * multires and tuple(got.shape) == (4, 333, dim)
         assert torch.equal(got[..., :3].cpu(), xyz)
         assert (got.cpu() - want).abs().max() <= 2e-6      # sinf/cosf of arguments up to 2^9: a few ulp
+
+
+def test_pipelined_batch_equals_one_call_per_sample(dev, tmp_path):
+    """mesh.create_meshes_pipelined (bind / grid passes / mesh extraction of consecutive samples overlapped
+    on three threads and streams) writes byte-identical files to the one-call-per-sample loop."""
+    dec = synthetic.make_decoder(0)
+    samples = [synthetic.make_sample(i) for i in range(5)]
+    N = 40
+    seq = []
+    for i, s in enumerate(samples):
+        sc = s.to(dev)
+        seq.append(amesh.create_mesh_combined_decoder(True, True, False, dec, sc.latent, sc.mano_results, sc.obj_results,
+                                                      None, sc.specs, str(tmp_path / f"seq{i}"), N=N))
+    got = amesh.create_meshes_pipelined(dec, samples, [str(tmp_path / f"pipe{i}") for i in range(5)], N=N)
+    assert len(got) == 5
+    for i in range(5):
+        for tag in ("hand", "obj"):
+            a, b = tmp_path / f"seq{i}_{tag}.ply", tmp_path / f"pipe{i}_{tag}.ply"
+            assert os.path.exists(a) == os.path.exists(b)
+            if os.path.exists(a):
+                assert open(a, "rb").read() == open(b, "rb").read()
+                assert np.array_equal(seq[i][tag].faces, got[i][tag].faces)
+                assert np.array_equal(seq[i][tag].vertices, got[i][tag].vertices)
