@@ -63,9 +63,9 @@ constexpr int64_t kSampleBytes = (int64_t)2 * 2 * kPTilesPerDecoder * kTileBytes
 constexpr int kOffALo = 0;
 constexpr int kApBytes = kRows * 16 * 2;                          // point operand: 128 rows x 16 k, no swizzle (4 KiB)
 constexpr int kOffAP = kOffALo + 8 * kSlotBytes;                 // 131072
-constexpr int kOffRing = kOffAP + kApBytes;                      // 135168 (1024-aligned)
-constexpr int kOffW4 = kOffRing + kRing * kSlotTileBytes;        // 217088
-constexpr int kOffRed = kOffW4 + 512 * 4;
+constexpr int kOffRing = kOffAP + 2 * kApBytes;                  // 139264 (1024-aligned); AP is double-buffered per item
+constexpr int kOffW4 = kOffRing + kRing * kSlotTileBytes;        // 221184: w4 of BOTH decoders, loaded once
+constexpr int kOffRed = kOffW4 + 2 * 512 * 4;
 constexpr int kOffBar = kOffRed + 2 * kRows * 4;
 constexpr int kBarFull = 0;
 constexpr int kBarFullLocal = kBarFull + kRing;
@@ -74,7 +74,8 @@ constexpr int kBarAFull = kBarEmpty + kRing;           // [8] K positions
 constexpr int kBarTmemFull = kBarAFull + 8;            // [2]
 constexpr int kBarTmemEmpty = kBarTmemFull + 2;        // [2]
 constexpr int kBarApFull = kBarTmemEmpty + 2;          // [1]
-constexpr int kNumBars = kBarApFull + 1;
+constexpr int kBarPosFree = kBarApFull + 1;            // [2] K positions {0,1} / {2,3} no longer read by layer 3
+constexpr int kNumBars = kBarPosFree + 2;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 constexpr int kSmemBytesDebug = kSmemBytes + 266 * 8;      // + fine-grained wait counters of the debug build
@@ -214,14 +215,25 @@ struct Args {
   float* out_obj;
   int32_t* bbox;
   int32_t* status;         // [0] |= 1 when an activation exceeded the fp8 operand range
+  int32_t items_base, items_rem;   // 256-point items per CTA pair: items_base (+1 for the first items_rem pairs)
   long long* dbg;          // optional int64[512] of cycle counters of CTA pair 0 (tools/tc3_phase_timing.py)
   int dbg_flags;           // debug build only (results become garbage): 1 = no A8 stores, 2 = no weight copies,
-                           // 4 = no fp8 UMMAs, 8 = no fp16 main UMMAs, 16 = no epilogue math, 32 = fine-grained wait counters
+                           // 4 = no fp8 UMMAs, 8 = no fp16 main UMMAs, 16 = no epilogue math (64: layer 0 only), 32 = fine-grained wait counters
 };
 
-// N-block schedule of one work item: layer, number of 64-wide K chunks, K position of chunk j
+// N-block schedule of one decoder instance (one decoder for one 256-point item): 14 N blocks g, their layer,
+// number of 64-wide K chunks and accumulator buffer.
+//
+// Layer 0 has no K chunks (its N blocks are a single K=16 UMMA), so it is pure epilogue.  To keep the tensor pipe
+// busy meanwhile, the first two layer-0 blocks of instance s+1 are issued INSIDE the last N block of layer 3 of
+// instance s (after its chunks 2 and 5): that block reads the K positions in natural order and commits
+// pos_free[0] / pos_free[1] once positions {0,1} / {2,3} have been consumed, after which the layer-0 epilogues
+// of the next instance may overwrite them.  Accumulator buffers are therefore not strictly alternating; per
+// instance (in issue order g = 0..13): X X X Y | X Y | X Y X Y | X Y X Y -- 8 uses of X and 6 of Y, so the
+// barrier parities repeat every instance.
 __device__ __forceinline__ int nb_layer(int g) { return g < 4 ? 0 : (g < 6 ? 1 : (g < 10 ? 2 : 3)); }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 0 ? 0 : (layer == 2 ? 4 : 8); }
+__device__ __forceinline__ int buf_of(int g) { return g < 3 ? 0 : (g == 3 ? 1 : (g & 1)); }
 
 template <bool kDebug>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eval_kernel(const Args a) {
@@ -242,6 +254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
     for (int i = 0; i < 8; ++i) mbar_init(bar(kBarAFull + i), 16);     // 4 warps x 2 lanes x 2 CTAs
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarTmemFull + i), 1); mbar_init(bar(kBarTmemEmpty + i), 16); }
     mbar_init(bar(kBarApFull), 8);                                    // 4 warps x 2 CTAs
+    for (int i = 0; i < 2; ++i) mbar_init(bar(kBarPosFree + i), 1);
     fence_mbar_init();
   }
   __syncwarp();
@@ -258,9 +271,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
   const int64_t n_tiles = (total + kPtsPerTile - 1) / kPtsPerTile;
   const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
+  // instances handled by this CTA pair: (item, decoder) in order; item k of this pair is tile cluster_id + k n_clusters
+  // (no 64-bit division here: its subroutine call would hide from ptxas that the loop bounds are warp-uniform,
+  // and the issuer's descriptors would fall out of the uniform registers)
+  const int64_t n_items = a.items_base + (cluster_id < a.items_rem ? 1 : 0);
+  const int64_t n_inst = 2 * n_items;
+
   if (warp == kProducerWarp) {
     // =========================== weight-stream producer ===========================
-    if (lane == 0) {
+    // Pushes tiles in exactly the order the issuer consumes them (see the schedule above).
+    if (lane == 0 && n_inst > 0) {
       uint32_t slot = 0, phase = 0;
       auto push = [&](const uint8_t* src, uint32_t bytes) {
         mbar_wait(bar(kBarEmpty + slot), phase ^ 1);
@@ -273,14 +293,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
         }
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       };
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        for (int dec = 0; dec < 2; ++dec) {
-          const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * kMainTilesPerDecoder * kTileBytes;
-          const uint8_t* pt = a.samp + (int64_t)(dec * 2 + rank) * kPTilesPerDecoder * kTileBytes;
-          for (int g = 0; g < kPTilesPerDecoder; ++g) {
-            push(pt, kTileBytes); pt += kTileBytes;
-            const int n = layer_chunks(nb_layer(g));
-            for (int i = 0; i < n; ++i) { push(mt, kSlotTileBytes); mt += kSlotTileBytes; }   // hi + lo in one copy
+      auto ptile = [&](int dec, int g) { return a.samp + ((int64_t)(dec * 2 + rank) * kPTilesPerDecoder + g) * kTileBytes; };
+      push(ptile(0, 0), kTileBytes);
+      push(ptile(0, 1), kTileBytes);
+      for (int64_t s_i = 0; s_i < n_inst; ++s_i) {
+        const int dec = (int)(s_i & 1);
+        const bool has_next = s_i + 1 < n_inst;
+        const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * kMainTilesPerDecoder * kTileBytes;
+        for (int g = 2; g < kPTilesPerDecoder; ++g) {
+          push(ptile(dec, g), kTileBytes);
+          const int n = layer_chunks(nb_layer(g));
+          for (int j = 0; j < n; ++j) {
+            push(mt, kSlotTileBytes); mt += kSlotTileBytes;             // (fp16, fp8) pair in one copy
+            if (g == kPTilesPerDecoder - 1 && has_next) {
+              if (j == 2) push(ptile(dec ^ 1, 0), kTileBytes);
+              if (j == 5) push(ptile(dec ^ 1, 1), kTileBytes);
+            }
           }
         }
       }
@@ -291,92 +319,107 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
       // ======================= peer CTA: relay "my half of the tile landed" =======================
       if (lane == 0) {
         uint32_t slot = 0, phase = 0;
-        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-          for (int i = 0; i < 2 * kFillsPerItem; ++i) {
-            mbar_wait(bar(kBarFullLocal + slot), phase);
-            mbar_arrive_cluster(bar(kBarFull + slot), 0);
-            if (++slot == kRing) { slot = 0; phase ^= 1; }
-          }
+        const int64_t fills = n_inst * kFillsPerItem;
+        for (int64_t i = 0; i < fills; ++i) {
+          mbar_wait(bar(kBarFullLocal + slot), phase);
+          mbar_arrive_cluster(bar(kBarFull + slot), 0);
+          if (++slot == kRing) { slot = 0; phase ^= 1; }
         }
       }
       __syncwarp();
-    } else {
+    } else if (n_inst > 0) {
       // =================================== UMMA issuer ===================================
-      // The whole warp walks the schedule (all values warp-uniform -> uniform registers); lane 0
-      // issues the tcgen05 instructions.
-      const uint32_t issue = lane == 0 ? 1u : 0u;
+      // The whole warp walks the schedule (all values warp-uniform -> uniform registers); elect.sync inside the
+      // wrappers picks the issuing lane.
+      const uint32_t issue = 1u;
       uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
-      uint32_t nblk = 0;                                   // global N-block counter -> TMEM buffer + parities
+      // uses so far of accumulator buffer X / Y -- scalars, not an indexed array: an array goes to local memory
+      // and its (per-thread) loads make the wait loops, and then every descriptor, look divergent to ptxas
+      uint32_t cnt_x = 0, cnt_y = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
-      const uint32_t alo_lo = desc_lo(sb + kOffALo), ring_lo = desc_lo(sb + kOffRing), ap_addr = sb + kOffAP;
+      const uint32_t alo_lo = desc_lo(sb + kOffALo), ring_lo = desc_lo(sb + kOffRing);
       const uint32_t bar0 = sb + kOffBar;
       long long w_ring = 0, w_a = 0, w_acc = 0, t_begin = kDebug ? clock64() : 0;
-      int dbg_slot = 0;                                    // (g, fill) index of the wait being timed (debug build)
-      // fine-grained wait counters live in (otherwise unused) shared memory behind the TMEM pointer
-      long long* fine_cnt = reinterpret_cast<long long*>(smem + kOffTmemPtr + 16);
-      const bool fine = kDebug && (a.dbg_flags & 32) && cluster_id == 0 && issue;
-      if (fine) for (int z = 0; z < 266; ++z) fine_cnt[z] = 0;
-      auto take = [&]() -> uint32_t {                      // wait for the next ring tile, return its descriptor word
+      auto take = [&]() __attribute__((always_inline)) -> uint32_t {                      // wait for the next ring tile, return its descriptor word
         const long long t0 = kDebug ? clock64() : 0;
         mbar_wait(bar0 + 8 * (kBarFull + slot), phase);
-        if (kDebug) { const long long dt = clock64() - t0; w_ring += dt; if (fine) fine_cnt[dbg_slot] += dt; }
+        if (kDebug) w_ring += clock64() - t0;
         tc_fence_after();
         return ring_lo + slot * (kSlotTileBytes >> 4);
       };
-      auto release = [&]() {
+      auto release = [&]() __attribute__((always_inline)) {
         umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + slot));
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       };
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        mbar_wait(bar0 + 8 * kBarApFull, ap_phase); ap_phase ^= 1;
+      // start an N block in accumulator buffer `buf`: wait until its previous contents were drained, then the
+      // bias + point-term UMMA (K = 16) of the block against the point operand of `item`
+      auto begin_block = [&](int buf, uint32_t ap_sel) __attribute__((always_inline)) -> uint32_t {
+        const long long t0 = kDebug ? clock64() : 0;
+        mbar_wait(bar0 + 8 * (kBarTmemEmpty + buf), ((buf ? cnt_y : cnt_x) & 1u) ^ 1u);
+        if (kDebug) w_acc += clock64() - t0;
+        if (buf) ++cnt_y; else ++cnt_x;
         tc_fence_after();
-        for (int dec = 0; dec < 2; ++dec) {
-          for (int g = 0; g < kPTilesPerDecoder; ++g, ++nblk) {
-            const int layer = nb_layer(g);
-            const bool first_nb = g == 0 || g == 4 || g == 6 || g == 10;
-            const uint32_t buf = nblk & 1u, use = nblk >> 1;
-            const uint32_t d_tmem = tmem_u + buf * 128;
-            {
+        const uint32_t d_tmem = tmem_u + buf * 128;
+        const uint32_t b = take();
+        umma_ap(issue, d_tmem, sb + kOffAP + ap_sel * kApBytes, b, 0u);
+        release();
+        return d_tmem;
+      };
+      auto wait_ap = [&]() __attribute__((always_inline)) { mbar_wait(bar0 + 8 * kBarApFull, ap_phase); ap_phase ^= 1; tc_fence_after(); };
+      // prologue: the first two layer-0 blocks of instance 0
+      wait_ap();
+      for (int g = 0; g < 2; ++g) {
+        begin_block(0, 0);
+        umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + 0));
+      }
+      const int n_inst32 = (int)n_inst;
+      for (int s_i = 0; s_i < n_inst32; ++s_i) {
+        const uint32_t ap_sel = (uint32_t)(s_i >> 1) & 1u;         // AP buffer of this instance's item
+        const bool has_next = s_i + 1 < n_inst32;
+        for (int g = 2; g < kPTilesPerDecoder; ++g) {
+          const int layer = nb_layer(g);
+          const bool first_nb = g == 4 || g == 6 || g == 10;
+          const bool last_blk = g == kPTilesPerDecoder - 1;
+          const int buf = buf_of(g);
+          const uint32_t d_tmem = begin_block(buf, ap_sel);
+          const int nch = layer_chunks(layer);
+          for (int j = 0; j < nch; ++j) {
+            // layer 3 reads x3 as it becomes available (positions 4..7 first), except in its last block
+            const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
+            if (first_nb) {
               const long long t0 = kDebug ? clock64() : 0;
-              mbar_wait(bar0 + 8 * (kBarTmemEmpty + buf), (use & 1u) ^ 1u);
-              if (kDebug) { const long long dt = clock64() - t0; w_acc += dt; if (fine) fine_cnt[252 + g] += dt; }
+              mbar_wait(bar0 + 8 * (kBarAFull + pos), (a_phase >> pos) & 1u);
+              if (kDebug) w_a += clock64() - t0;
+              a_phase ^= 1u << pos;
+              tc_fence_after();
             }
-            tc_fence_after();
-            {   // bias + point term: K = 16
-              if (kDebug) dbg_slot = g * 9;
-              const uint32_t b = take();
-              umma_ap(issue, d_tmem, ap_addr, b, 0u);
-              release();
-            }
-            const int nch = layer_chunks(layer);
-            for (int j = 0; j < nch; ++j) {
-              const int pos = layer == 3 ? ((j + 4) & 7) : j;
-              if (first_nb) {
-                const long long t0 = kDebug ? clock64() : 0;
-                mbar_wait(bar0 + 8 * (kBarAFull + pos), (a_phase >> pos) & 1u);
-                if (kDebug) { const long long dt = clock64() - t0; w_a += dt; if (fine) fine_cnt[126 + g * 9 + 1 + j] += dt; }
-                a_phase ^= 1u << pos;
-                tc_fence_after();
-              }
-              const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
-              const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
-              if (kDebug) dbg_slot = g * 9 + 1 + j;
-              const uint32_t b = take();                       // (fp16, fp8) tile pair
+            const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
+            const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
+            const uint32_t b = take();                       // (fp16, fp8) tile pair
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {                 // TMEM-A and SMEM-A forms alternate: evens out the smem reads
-                if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
-                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b + (kTileBytes >> 4) + ks * 2, 1u);
-              }
-              release();
+            for (int ks = 0; ks < 4; ++ks) {                 // TMEM-A and SMEM-A forms alternate: evens out the smem reads
+              if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
+              if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b + (kTileBytes >> 4) + ks * 2, 1u);
             }
-            umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
+            release();
+            if (last_blk && has_next) {
+              // positions {0,1} / {2,3} consumed -> the next instance's layer-0 epilogues may overwrite them;
+              // and its first two layer-0 blocks are issued here, into buffer X, while this block keeps Y busy
+              if (j == 1) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 0));
+              if (j == 3) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 1));
+              if (j == 2 || j == 5) {
+                if (j == 2 && ((s_i + 1) & 1) == 0) wait_ap();          // next instance starts a new item
+                begin_block(0, (uint32_t)((s_i + 1) >> 1) & 1u);
+                umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + 0));
+              }
+            }
           }
+          umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
         }
       }
-      if (kDebug && cluster_id == 0 && issue) {
+      if (kDebug && cluster_id == 0 && lane == 0) {
         a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_a; a.dbg[2] = w_ring; a.dbg[3] = w_acc;
-        if (fine) for (int z = 0; z < 266; ++z) a.dbg[32 + z] = fine_cnt[z];
       }
       __syncwarp();
     }
@@ -392,9 +435,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
     const float* sparams = reinterpret_cast<const float*>(a.stat + kWeightBytes);
     const float* sscal = reinterpret_cast<const float*>(a.samp + (int64_t)2 * 2 * kPTilesPerDecoder * kTileBytes);
     const float cp = __ldg(sscal + 2), c1 = __ldg(sscal + 3);
-    uint32_t nblk = 0;
-    auto wait_full = [&](uint32_t n) {
-      mbar_wait(bar(kBarTmemFull + (n & 1u)), (n >> 1) & 1u);
+    uint32_t cnt_x = 0, cnt_y = 0;                 // uses so far of accumulator buffer X / Y (same sequence as the issuer)
+    uint32_t posfree_phase = 0;
+    // w4 of both decoders stays in shared memory for the whole kernel
+    for (int z = et; z < 1024; z += kEpiThreads)
+      sts_f1(sW4 + 4 * z, __ldg(sparams + (size_t)(z >> 9) * kStaticParamFloats + (z & 511)));
+    epi_bar_sync();
+    auto wait_full = [&](int buf) {                // wait for the next completion of buffer `buf` (does not consume it)
+      mbar_wait(bar(kBarTmemFull + buf), (buf ? cnt_y : cnt_x) & 1u);
       tc_fence_after();
     };
     // relu + split of 32 accumulator columns -> 16 hi16 words (pairs k, k+1), 8 lo8 words and 8 x8 words (k..k+3)
@@ -440,10 +488,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
       __syncwarp();
       if (lane < 2) mbar_arrive_cluster(bar(kBarAFull + pos), 0);
     };
-    auto free_acc = [&](uint32_t n) {              // this warp is done reading accumulator buffer n&1
+    auto free_acc = [&](int buf) {                 // this warp is done reading accumulator buffer `buf`
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar(kBarTmemEmpty + (n & 1u)), 0);
+      if (lane == 0) mbar_arrive_cluster(bar(kBarTmemEmpty + buf), 0);
+    };
+    // point operand of item k -> AP[k & 1] (rows written by the ch == 0 warps)
+    auto write_ap = [&](int64_t k) {
+      if (ch != 0) return;
+      const int64_t i = a.q.begin + (cluster_id + k * n_clusters) * kPtsPerTile + rank * kRows + row;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (i < a.q.end) {
+        if (a.q.mode == ASDF_QUERY_POINTS) {
+          const float* r = a.q.points_dev + (size_t)i * a.q.point_stride;
+          px = __ldg(r); py = __ldg(r + 1); pz = __ldg(r + 2);
+        } else {
+          grid_point(i, a.q.N, a.q.mode, a.q.voxel, a.q.origin[0], a.q.origin[1], a.q.origin[2], px, py, pz);
+        }
+      }
+      const float sx = px * cp, sy = py * cp, sz = pz * cp;
+      const __half2 hxy = __floats2half2_rn(sx, sy), hz1 = __floats2half2_rn(sz, c1);
+      const float2 fxy = __half22float2(hxy);
+      const float fz = __low2float(hz1);
+      const __half2 lxy = __floats2half2_rn(sx - fxy.x, sy - fxy.y), lz0 = __floats2half2_rn(sz - fz, 0.f);
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&hxy), w1 = *reinterpret_cast<const uint32_t*>(&hz1);
+      const uint32_t w2 = *reinterpret_cast<const uint32_t*>(&lxy), w3 = *reinterpret_cast<const uint32_t*>(&lz0);
+      const uint32_t base = sbase + kOffAP + (uint32_t)(k & 1) * kApBytes + (row >> 3) * 256 + (row & 7) * 16;
+      sts_u4(base, make_uint4(w0, w1, w2, w3));             // k 0..7 : p_hi, c1, p_lo, 0
+      sts_u4(base + 128, make_uint4(w0, w1, 0u, 0u));       // k 8..15: p_hi, c1, 0
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar(kBarApFull), 0);
     };
 
     long long ph[16];
@@ -451,103 +526,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc3_eva
     const bool stamp = kDebug && cluster_id == 0 && rank == 0 && et == 0;
     long long tlast = kDebug ? clock64() : 0;
 #define ASDF_STAMP2(k) do { if (stamp) { const long long _t = clock64(); ph[k] += _t - tlast; tlast = _t; } } while (0)
-    for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-      const int64_t i = a.q.begin + t * kPtsPerTile + rank * kRows + row;
+    float part = 0.f;
+    // one N block of layers 0..2 of decoder `dec`: accumulator -> relu -> (hi16, lo8, x8) of the next layer's input.
+    // `windowed`: a layer-0 block of the NEXT instance processed while layer 3 of the current one still runs: its
+    // stores wait until layer 3 has consumed the target positions.
+    auto hidden_block = [&](int dec, int g, bool windowed) {
+      const int layer = nb_layer(g);
+      const int nb = g - (layer == 0 ? 0 : (layer == 1 ? 4 : 6));
+      const int buf = buf_of(g);
+      const float* sp = sparams + (size_t)dec * kStaticParamFloats + 512;
+      const float inv = layer == 0 ? __ldg(sscal + dec) : __ldg(sp + layer);
+      const uint32_t acc_addr = tmem_base + lane_addr + buf * 128 + ch * 64;
+      ASDF_STAMP2(8 + layer);
+      wait_full(buf);
+      if (buf) ++cnt_y; else ++cnt_x;
+      ASDF_STAMP2(layer);
+      // feature chunk 2*nb + ch of the layer output -> K position of the next layer's input
+      const int cidx = 2 * nb + ch;
+      const int pos = layer == 2 ? ((cidx + 4) & 7) : cidx;
+      // blocks whose target positions are still being read by this layer's remaining UMMAs
+      const bool hold = (layer == 1 && nb == 0) || (layer == 2 && nb == 2);
+      uint32_t hi[2][16] = {}, lo8[2][8] = {}, x8[2][8] = {};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float acc[32];
+        tmem_ld32(acc_addr + h * 32, acc);
+        tmem_ld_wait();
+        if (!(kDebug && ((a.dbg_flags & 16) || ((a.dbg_flags & 64) && layer == 0)))) split32(acc, inv, hi[h], lo8[h], x8[h]);
+      }
+      free_acc(buf);
+      ASDF_STAMP2(8 + layer);
+      if (hold) wait_full(buf_of(g + 1));           // all UMMAs of this layer have retired
+      if (windowed) { mbar_wait(bar(kBarPosFree + nb), posfree_phase); tc_fence_after(); }
+      ASDF_STAMP2(4 + layer);
+      store_half(pos, 0, hi[0], lo8[0], x8[0]);
+      store_half(pos, 1, hi[1], lo8[1], x8[1]);
+      publish(pos);
+    };
+    auto l3_block = [&](int dec, int g) {
+      const int nb = g - 10, buf = buf_of(g);
+      const float inv3 = __ldg(sparams + (size_t)dec * kStaticParamFloats + 512 + 3);
+      const uint32_t acc_addr = tmem_base + lane_addr + buf * 128 + ch * 64;
+      ASDF_STAMP2(11);
+      wait_full(buf);
+      if (buf) ++cnt_y; else ++cnt_x;
+      ASDF_STAMP2(3);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float acc[32];
+        tmem_ld32(acc_addr + h * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 w = lds_f4(sW4 + 4 * (512 * dec + 128 * nb + 64 * ch + 32 * h + 4 * j4));
+          part = fmaf(fmaxf(acc[4 * j4 + 0] * inv3, 0.f), w.x, part);
+          part = fmaf(fmaxf(acc[4 * j4 + 1] * inv3, 0.f), w.y, part);
+          part = fmaf(fmaxf(acc[4 * j4 + 2] * inv3, 0.f), w.z, part);
+          part = fmaf(fmaxf(acc[4 * j4 + 3] * inv3, 0.f), w.w, part);
+        }
+      }
+      free_acc(buf);
+    };
+
+    if (n_inst > 0) {
+      write_ap(0);
+      hidden_block(0, 0, false);
+      hidden_block(0, 1, false);
+    }
+    for (int64_t s_i = 0; s_i < n_inst; ++s_i) {
+      const int dec = (int)(s_i & 1);
+      const int64_t k = s_i >> 1;
+      const bool has_next = s_i + 1 < n_inst;
+      const int64_t i = a.q.begin + (cluster_id + k * n_clusters) * kPtsPerTile + rank * kRows + row;
       const bool live = i < a.q.end;
-      // ---------------- point operand AP (rows written by the ch == 0 warps) ----------------
+      // the next item's point operand, one instance ahead of its first use (the other AP buffer was last read by
+      // item k-1, whose UMMAs have all retired)
+      if (dec == 1 && k + 1 < n_items) write_ap(k + 1);
+      part = 0.f;
+      for (int g = 2; g < 10; ++g) hidden_block(dec, g, false);
+      for (int g = 10; g < 13; ++g) l3_block(dec, g);
+      if (has_next) {
+        hidden_block(dec ^ 1, 0, true);
+        hidden_block(dec ^ 1, 1, true);
+        posfree_phase ^= 1u;
+      }
+      l3_block(dec, 13);
+      ASDF_STAMP2(11);
+      epi_bar_sync();                              // the previous instance's readers of sRed are done
+      sts_f1(sRed + 4 * (ch * kRows + row), part);
+      epi_bar_sync();
       if (ch == 0) {
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (live) {
-          if (a.q.mode == ASDF_QUERY_POINTS) {
-            const float* r = a.q.points_dev + (size_t)i * a.q.point_stride;
-            px = __ldg(r); py = __ldg(r + 1); pz = __ldg(r + 2);
-          } else {
-            grid_point(i, a.q.N, a.q.mode, a.q.voxel, a.q.origin[0], a.q.origin[1], a.q.origin[2], px, py, pz);
-          }
-        }
-        const float sx = px * cp, sy = py * cp, sz = pz * cp;
-        const __half2 hxy = __floats2half2_rn(sx, sy), hz1 = __floats2half2_rn(sz, c1);
-        const float2 fxy = __half22float2(hxy);
-        const float fz = __low2float(hz1);
-        const __half2 lxy = __floats2half2_rn(sx - fxy.x, sy - fxy.y), lz0 = __floats2half2_rn(sz - fz, 0.f);
-        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&hxy), w1 = *reinterpret_cast<const uint32_t*>(&hz1);
-        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(&lxy), w3 = *reinterpret_cast<const uint32_t*>(&lz0);
-        const uint32_t base = sbase + kOffAP + (row >> 3) * 256 + (row & 7) * 16;
-        sts_u4(base, make_uint4(w0, w1, w2, w3));             // k 0..7 : p_hi, c1, p_lo, 0
-        sts_u4(base + 128, make_uint4(w0, w1, 0u, 0u));       // k 8..15: p_hi, c1, 0
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar(kBarApFull), 0);
+        const float b4 = __ldg(sparams + (size_t)dec * kStaticParamFloats + 512);
+        const float val = tanhf(lds_f1(sRed + 4 * row) + lds_f1(sRed + 4 * (kRows + row)) + b4);
+        if (live) (dec == 0 ? a.out_hand : a.out_obj)[i - a.q.begin] = val;
+        if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> dec & 1))
+          bbox_update(a.bbox + 6 * dec, live && val < 0.f, i, a.q.N);
       }
-      for (int dec = 0; dec < 2; ++dec) {
-        epi_bar_sync();                            // previous item's readers of sW4 / sRed are done
-        {
-          const float* sp = sparams + (size_t)dec * kStaticParamFloats;
-          sts_f1(sW4 + 4 * et, __ldg(sp + et)); sts_f1(sW4 + 4 * (et + 256), __ldg(sp + et + 256));
-        }
-        epi_bar_sync();
-        const float* sp = sparams + (size_t)dec * kStaticParamFloats + 512;
-        const float b4 = __ldg(sp), inv1 = __ldg(sp + 1), inv2 = __ldg(sp + 2), inv3 = __ldg(sp + 3);
-        const float inv0 = __ldg(sscal + dec);
-        float part = 0.f;
-        for (int g = 0; g < kPTilesPerDecoder; ++g, ++nblk) {
-          const int layer = nb_layer(g);
-          const int nb = g - (layer == 0 ? 0 : (layer == 1 ? 4 : (layer == 2 ? 6 : 10)));
-          const uint32_t acc_addr = tmem_base + lane_addr + (nblk & 1u) * 128 + ch * 64;
-          ASDF_STAMP2(8 + layer);                 // epilogue work attributed to the previous phase of this layer
-          wait_full(nblk);
-          ASDF_STAMP2(layer);                     // waiting for the accumulator of this layer
-          if (layer < 3) {
-            // feature chunk 2*nb + ch of the layer output -> K position of the next layer's input
-            const int cidx = 2 * nb + ch;
-            const int pos = layer == 2 ? ((cidx + 4) & 7) : cidx;
-            const float inv = layer == 0 ? inv0 : (layer == 1 ? inv1 : inv2);
-            // blocks whose target positions are still being read by this layer's remaining UMMAs
-            const bool hold = (layer == 1 && nb == 0) || (layer == 2 && nb == 2);
-            uint32_t hi[2][16] = {}, lo8[2][8] = {}, x8[2][8] = {};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float acc[32];
-              tmem_ld32(acc_addr + h * 32, acc);
-              tmem_ld_wait();
-              if (!(kDebug && (a.dbg_flags & 16))) split32(acc, inv, hi[h], lo8[h], x8[h]);
-            }
-            free_acc(nblk);
-            ASDF_STAMP2(8 + layer);
-            if (hold) wait_full(nblk + 1);          // all UMMAs of this layer have retired
-            ASDF_STAMP2(4 + layer);
-            store_half(pos, 0, hi[0], lo8[0], x8[0]);
-            store_half(pos, 1, hi[1], lo8[1], x8[1]);
-            publish(pos);
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float acc[32];
-              tmem_ld32(acc_addr + h * 32, acc);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w = lds_f4(sW4 + 4 * (128 * nb + 64 * ch + 32 * h + 4 * j4));
-                part = fmaf(fmaxf(acc[4 * j4 + 0] * inv3, 0.f), w.x, part);
-                part = fmaf(fmaxf(acc[4 * j4 + 1] * inv3, 0.f), w.y, part);
-                part = fmaf(fmaxf(acc[4 * j4 + 2] * inv3, 0.f), w.z, part);
-                part = fmaf(fmaxf(acc[4 * j4 + 3] * inv3, 0.f), w.w, part);
-              }
-            }
-            free_acc(nblk);
-          }
-        }
-        ASDF_STAMP2(11);
-        sts_f1(sRed + 4 * (ch * kRows + row), part);
-        epi_bar_sync();
-        if (ch == 0) {
-          const float val = tanhf(lds_f1(sRed + 4 * row) + lds_f1(sRed + 4 * (kRows + row)) + b4);
-          if (live) (dec == 0 ? a.out_hand : a.out_obj)[i - a.q.begin] = val;
-          if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> dec & 1))
-            bbox_update(a.bbox + 6 * dec, live && val < 0.f, i, a.q.N);
-        }
-        ASDF_STAMP2(12);
-      }
+      ASDF_STAMP2(12);
     }
     {   // any activation beyond the fp8 operand range (or non-finite)?  -> host falls back to k1_tc2.cu
       const float2 m = __half22float2(vmax2);
@@ -613,6 +688,7 @@ extern "C" int asdf_tc3_eval_debug(const void* static_dev, const void* sample_de
   a.q = *q; a.stat = (const uint8_t*)static_dev; a.samp = (const uint8_t*)sample_dev;
   a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.bbox = bbox_dev; a.status = status_dev; a.dbg = (long long*)debug_dev;
   a.dbg_flags = dbg_flags_env ? atoi(dbg_flags_env) : 0;
+  a.items_base = (int32_t)(n_tiles / clusters); a.items_rem = (int32_t)(n_tiles % clusters);
   if (debug_dev)
     tc3::tc3_eval_kernel<true><<<(unsigned)(2 * clusters), tc3::kThreads, tc3::kSmemBytesDebug, (cudaStream_t)stream>>>(a);
   else

@@ -1,7 +1,10 @@
 """Packing for the v3 tcgen05 kernel (csrc/k1_tc3.cu): fp16 main product + fp8 (e4m3) corrections.
 
 Static stream (bytes): main weight tiles ``[decoder][cta rank][128 tiles]`` of 8 KiB in the v2 order
-(tc2_pack.py: L1 nb 0..1 x kc 0..7, L2 nb 0..3 x kc 0..3, L3 nb 0..3 x j 0..7), alternating
+(tc2_pack.py: L1 nb 0..1 x kc 0..7, L2 nb 0..3 x kc 0..3, L3 nb 0..3 x j 0..7) -- except that the LAST N
+block of layer 3 stores its K chunks in the order kc = (j + 4) % 8: x3's chunk c lives at K position
+(c + 4) % 8, and that block walks the positions 0..7 in natural order so that positions 0..3 are released
+early for the next decoder's layer-0 epilogues (k1_tc3.cu) -- alternating
     fp16 tile   shared-memory image (K-major, 128B swizzle) of 64 rows x 64 k of  hi16(s_l W_l)
     fp8 tile    shared-memory image of 64 rows x 128 B: bytes 0..63  = e4m3(2^-10 s_l W_l[k]),
                                                        bytes 64..127 = e4m3((s_l W_l - hi16(s_l W_l))[k])
@@ -81,7 +84,8 @@ def pack_static_numpy(topo):
             for W, sc, nbs, kcs in ((W1, s[0], 2, 8), (W2, s[1], 4, 4), (W3, s[2], 4, 8)):
                 for nb in range(nbs):
                     r0 = 128 * nb + 64 * c
-                    for kc in range(kcs):
+                    for j in range(kcs):
+                        kc = (j + 4) % 8 if (W is W3 and nb == nbs - 1) else j
                         blk = (sc * W[r0:r0 + 64, 64 * kc:64 * kc + 64]).astype(np.float64)
                         hi = blk.astype(np.float16)
                         lo = blk - hi.astype(np.float64)

@@ -78,8 +78,10 @@ def emulate(raw_static, raw_sample, xyz, want_max=False):
         store(l1, inv1, lambda c: c)
         l2 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8, range(4)) for _ in range(4)], 1).astype(np.float32)
         store(l2, inv2, lambda c: (c + 4) % 8)
-        l3 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8, [(j + 4) % 8 for j in range(8)])
-                             for _ in range(4)], 1)
+        # layer 3 reads positions 4..7 first, except its last N block (natural order, chunks permuted in the stream)
+        l3 = np.concatenate([main_acc(ptile_acc(), a_hi, a_lo8, a_x8,
+                                      [(j + 4) % 8 for j in range(8)] if nb < 3 else list(range(8)))
+                             for nb in range(4)], 1)
         assert mi[0] == T.MAIN_TILES and pi[0] == T.P_TILES
         x4 = np.maximum(l3.astype(np.float32) * np.float32(inv3), 0).astype(np.float32)
         s4 = (x4.astype(np.float64) @ w4.astype(np.float64)).astype(np.float32)

@@ -23,6 +23,11 @@ hand = torch.empty(N ** 3, device=dev); obj = torch.empty(N ** 3, device=dev)
 dbg = torch.zeros(512, dtype=torch.int64, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+REPS = int(os.environ.get("ASDF_TC3_REPS", 1))
+for _ in range(REPS - 1):       # long enough to reach the power-capped steady state
+    _lib.check(_lib.lib().asdf_tc3_eval_debug(_lib.ptr(bound.engine.tc3_static), _lib.ptr(tc2.sample), C.byref(q),
+                                              _lib.ptr(hand), _lib.ptr(obj), None, _lib.ptr(status), _lib.stream_ptr(dev), _lib.ptr(dbg)), "dbg")
+dbg.zero_()
 e0.record()
 _lib.check(_lib.lib().asdf_tc3_eval_debug(_lib.ptr(bound.engine.tc3_static), _lib.ptr(tc2.sample), C.byref(q),
                                           _lib.ptr(hand), _lib.ptr(obj), None, _lib.ptr(status), _lib.stream_ptr(dev), _lib.ptr(dbg)), "dbg")
