@@ -91,14 +91,37 @@ __global__ void cc_stats(const CcStatsArgs a) {
   const int root = a.parent[ia];
   const unsigned fa = plane_bits(a.verts_local, ia, a.last), fb = plane_bits(a.verts_local, ib, a.last),
                  fc = plane_bits(a.verts_local, ic, a.last);
-  if (((fa & fb) | (fb & fc) | (fc & fa)) != 0u) atomicOr(a.open + root, 1);
   const double ax = a.points[3 * ia], ay = a.points[3 * ia + 1], az = a.points[3 * ia + 2];
   const double e1x = a.points[3 * ib] - ax, e1y = a.points[3 * ib + 1] - ay, e1z = a.points[3 * ib + 2] - az;
   const double e2x = a.points[3 * ic] - ax, e2y = a.points[3 * ic + 1] - ay, e2z = a.points[3 * ic + 2] - az;
   const double cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
-  atomicAdd(a.area + root, 0.5 * sqrt(cx * cx + cy * cy + cz * cz));
-  atomicAdd(a.nfaces + root, 1);
-  atomicMin(a.first_face + root, (int)f);
+  double area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+  const bool open = ((fa & fb) | (fb & fc) | (fc & fa)) != 0u;
+  // Almost every warp sees a single component: aggregate in the warp and issue one set of atomics (thousands of
+  // faces hammering the same four addresses serialise in L2 otherwise).
+  const unsigned active = __activemask();
+  const unsigned same = __match_any_sync(active, root);
+  if (same == active) {
+    const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+    int cnt = __popc(active);
+    const int any_open = __any_sync(active, open);
+    const int first = __reduce_min_sync(active, (int)f);
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_down_sync(active, area, off);
+      if (lane + off < 32 && (active >> (lane + off) & 1u)) area += o;
+    }
+    if (lane == leader) {
+      atomicAdd(a.area + root, area);
+      atomicAdd(a.nfaces + root, cnt);
+      atomicMin(a.first_face + root, first);
+      if (any_open) atomicOr(a.open + root, 1);
+    }
+  } else {
+    if (open) atomicOr(a.open + root, 1);
+    atomicAdd(a.area + root, area);
+    atomicAdd(a.nfaces + root, 1);
+    atomicMin(a.first_face + root, (int)f);
+  }
 }
 
 // keep_v[v] = parent[v] == best;  keep_f[f] = parent[faces[f][0]] == best   (int32 0/1 for the caller's scan)
