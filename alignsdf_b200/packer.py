@@ -68,6 +68,7 @@ class Topology:
     layers: dict = field(default_factory=dict)      # prefix -> [(W, b)]
     layer_norms: dict = field(default_factory=dict) # prefix -> [None | (gamma, beta)]  (LayerNorm before the ReLU)
     classifier: tuple | None = None                 # (Wc, bc)
+    f32_cache: dict = field(default_factory=dict, repr=False)   # (prefix, layer, shape) -> f32 copy of the static weights
 
 
 def decoder_topology(decoder) -> Topology:
@@ -259,8 +260,13 @@ def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
             ln = topo.layer_norms.get(prefix, [None] * len(folded))[l]
             fl.ln = None if ln is None else (np.ascontiguousarray(ln[0], dtype=np.float32),
                                              np.ascontiguousarray(ln[1], dtype=np.float32))
-        for fl in folded:
-            fl.Wx = None if fl.Wx is None else np.ascontiguousarray(fl.Wx, dtype=np.float32)
+        for l, fl in enumerate(folded):
+            if fl.Wx is not None:                  # static per decoder: convert once, not once per sample
+                key = (prefix, l, fl.Wx.shape)
+                cached = topo.f32_cache.get(key)
+                if cached is None:
+                    cached = topo.f32_cache[key] = np.ascontiguousarray(fl.Wx, dtype=np.float32)
+                fl.Wx = cached
             fl.M = None if fl.M is None else np.ascontiguousarray(fl.M, dtype=np.float32)
             fl.B = np.ascontiguousarray(fl.B, dtype=np.float32)
         out.append(FoldedBranch(tag, folded, D))

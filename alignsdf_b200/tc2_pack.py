@@ -132,7 +132,7 @@ def pack_sample_numpy(branches, scales, p_absmax=1.25, act_scale=ACT_SCALE):
                       (act_scale * scales[d][1], L[2].M.astype(np.float64), L[2].B.astype(np.float64)),
                       (act_scale * scales[d][2], None, L[3].B.astype(np.float64))])
     cp, c1, S0 = choose_point_scales(terms, p_absmax)
-    tiles = np.zeros((2, 2, P_TILES, TILE_ELEMS), np.float16)
+    rows = np.zeros((2, 2, P_TILES, ROWS, TK), np.float16)      # [decoder][cta rank][N block][row][k], unswizzled
     for d in range(2):
         g = 0
         for l, (S, M, B) in enumerate(terms[d]):
@@ -148,11 +148,12 @@ def pack_sample_numpy(branches, scales, p_absmax=1.25, act_scale=ACT_SCALE):
             full[:, 0:3], full[:, 3] = mh, bh
             full[:, 4:7] = mh
             full[:, 8:11], full[:, 11] = ml, bl
-            for nb in range(n // 128):
-                for c in range(2):
-                    tiles[d, c, g] = swizzle_tile(full[128 * nb + 64 * c:128 * nb + 64 * c + 64])
-                g += 1
+            nbs = n // 128
+            rows[d, :, g:g + nbs] = full.reshape(nbs, 2, ROWS, TK).transpose(1, 0, 2, 3)
+            g += nbs
         assert g == P_TILES
+    tiles = np.zeros((2, 2, P_TILES, TILE_ELEMS), np.float16)   # all 56 tiles swizzled in one scatter
+    tiles[..., _swz().reshape(-1)] = rows.reshape(2, 2, P_TILES, TILE_ELEMS)
     scal = np.zeros(16, np.float32)
     scal[0], scal[1] = act_scale / S0[0], act_scale / S0[1]
     scal[2], scal[3] = cp, c1
