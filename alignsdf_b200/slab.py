@@ -28,11 +28,30 @@ import torch.distributed as dist
 INT_MAX = 2 ** 31 - 1
 
 
-def slab_planes(N: int, rank: int, world: int):
-    """Planes [z0, z1) of axis 0 owned by ``rank`` (as even as possible, contiguous)."""
-    base, rem = divmod(N, world)
-    z0 = rank * base + min(rank, rem)
-    return z0, z0 + base + (1 if rank < rem else 0)
+def slab_planes(N: int, rank: int, world: int, relief: int = 0):
+    """Planes [z0, z1) of axis 0 owned by ``rank`` (as even as possible, contiguous).  ``relief`` planes are
+    taken off rank 0 and spread over the others: rank 0 also gathers and stitches the mesh pieces, and with
+    back-to-back samples that tail would otherwise make every other rank wait at the next collective."""
+    if relief <= 0 or world < 2:
+        base, rem = divmod(N, world)
+        z0 = rank * base + min(rank, rem)
+        return z0, z0 + base + (1 if rank < rem else 0)
+    first = max(N // world - relief, 1)
+    if rank == 0:
+        return 0, first
+    base, rem = divmod(N - first, world - 1)
+    r = rank - 1
+    z0 = first + r * base + min(r, rem)
+    return z0, z0 + base + (1 if r < rem else 0)
+
+
+def default_relief(N: int, world: int) -> int:
+    """Planes to take off rank 0 (see slab_planes): the gather + stitch tail is worth ~3.4 planes of two
+    passes at any N (both scale with N^2), shared with the other ranks -> 3.4 (world-1)/world, if slabs are thick
+    enough for it not to matter otherwise."""
+    if world < 2 or N // world < 16:
+        return 0
+    return int(round(3.4 * (world - 1) / world))
 
 
 @dataclass
@@ -42,6 +61,7 @@ class Backend:
     eval: callable
     mc: callable
     device: torch.device
+    relief: int = 0            # planes taken off rank 0 (slab_planes)
 
 
 def reduce_bbox(box: torch.Tensor, group=None) -> torch.Tensor:
@@ -128,7 +148,7 @@ def two_pass_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=T
     """Both evaluation passes on this rank's slab.  Returns dict(hand, obj [nz,N,N], voxel, origin,
     z0, z1) -- ``voxel``/``origin`` identical on every rank."""
     from .mesh import _bbox_to_minmax, _regrid
-    z0, z1 = slab_planes(N, rank, world)
+    z0, z1 = slab_planes(N, rank, world, backend.relief)
     mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
     vs1 = 2.0 / (N - 1)
     _, _, box = backend.eval(z0 * N * N, z1 * N * N, vs1, [-1.0, -1.0, -1.0], mask)
@@ -196,7 +216,8 @@ def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
                                   check_range=False)
         return r["verts"], r["points"], r["faces"], r["keys"]
 
-    return Backend(ev, mc, bound.device)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    return Backend(ev, mc, bound.device, default_relief(N, world))
 
 
 def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,

@@ -60,6 +60,7 @@ def _worker(rank, world, port, name, out_dir):
         meta, g, dec, sample = helpers.load_case(name)
         N = meta["N"]
         be = _oracle_backend(dec, sample, N)
+        be.relief = 2 if world == 3 else 0          # uneven slabs must give the identical result
         fields = slab.two_pass_slab(be, N, rank, world)
         meshes = slab.mesh_slab(be, fields, N, rank, world)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=float(fields["voxel"]),
@@ -78,6 +79,15 @@ def test_slab_planes_partition():
         assert cuts[0][0] == 0 and cuts[-1][1] == N
         assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
         assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    # rank-0 relief: still a contiguous partition, rank 0 thinner, the others even among themselves
+    for N, w, relief in ((256, 8, 3), (256, 2, 2), (48, 4, 3), (10, 4, 5)):
+        cuts = [slab.slab_planes(N, r, w, relief) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == N
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        assert cuts[0][1] - cuts[0][0] == max(N // w - relief, 1)
+        rest = [b - a for a, b in cuts[1:]]
+        assert max(rest) - min(rest) <= 1
+    assert slab.default_relief(256, 8) == 3 and slab.default_relief(256, 2) == 2 and slab.default_relief(32, 8) == 0
 
 
 @pytest.mark.parametrize("world", [2, 3])
