@@ -38,6 +38,7 @@ F_MIN = 2_086_912          # algorithmic FLOP per hand+obj query after folding (
 F_REF = 3_147_776          # FLOP per query as the reference executes it
 N_SAMPLES = 16             # BASELINE config #3: batch of 16 synthetic latents / poses
 NCU_TRAFFIC_BYTES = None   # filled from profiles/ by _ncu_traffic()
+STEP_SYNC = os.environ.get("ALIGNSDF_BENCH_STEP_SYNC", "0") == "1"
 
 
 def _ncu_traffic():
@@ -70,6 +71,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("ALIGNSDF_BENCH_NO_CLOCKS"):        # diagnostic: is the sampler itself perturbing the run?
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -217,6 +220,8 @@ def main():
             be = slab.gpu_backend(bound, N)
             fields = slab.two_pass_slab(be, N, rank, world)
             slab.mesh_slab(be, fields, N, rank, world)
+            if STEP_SYNC:
+                torch.cuda.synchronize(dev)
 
     def bind(i):
         s = host_samples[i % N_SAMPLES].to(dev)
