@@ -229,6 +229,12 @@ def main():
 
     # ---------------- device-resident timing ----------------
     bounds = [bind(i) for i in range(N_SAMPLES)]
+    # untimed set-up: one pass over the batch, so that every sample's packed blocks exist and the caching
+    # allocator has seen every (sample-dependent) mesh buffer size -- otherwise the first visit of each sample,
+    # inside the timed region, pays cudaMalloc + device synchronisation on every rank (multi-rank runs varied
+    # between 27 and 50 ms per step at 4 GPUs, while the end-to-end leg that runs afterwards was stable)
+    for i in range(N_SAMPLES):
+        step_device(i, bounds[i])
     for i in range(W):
         step_device(i, bounds[i % N_SAMPLES])
     kernel_ms.clear()
