@@ -116,32 +116,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {     // K-major, 128B swizzle, SBO = 1024 B
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               :: "r"(d), "l"(a), "l"(b), "r"(kIdesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-               :: "r"(d), "r"(a_tmem), "l"(b), "r"(kIdesc), "r"(acc), "r"(0u) : "memory");
-}
-// Lean forms used by the issuer: operands are the LOW descriptor words (address >> 4); the high
+// UMMA wrappers of the issuer: operands are the LOW descriptor words (address >> 4); the high
 // word (SBO = 1024 B, version 1, 128B swizzle) is the constant 0x40004040.  All operands are
 // warp-uniform so ptxas keeps them in uniform registers (no R2UR waterfall per UMMA).
 // The whole (converged) issuer warp executes these wrappers; elect.sync picks the one lane that
 // issues.  ptxas knows an ELECT predicate selects a single lane and emits the UTC*MMA directly --
 // predicating on `lane == 0` instead made it wrap every UMMA in a VOTEU / ELECT / BRA.U.ANY
 // "for each active lane" loop (~50 cycles per UMMA: the issuer, not the tensor pipe, set the pace).
-__device__ __forceinline__ void umma_ss_lo(uint32_t issue, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-               "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-               "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-               :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(acc), "r"(0x40004040u), "r"(issue) : "memory");
-}
 // kind::f8f6f4 (e4m3 x e4m3, K = 32 per instruction), both operands from shared memory
 __device__ __forceinline__ void umma_ss8_lo(uint32_t issue, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -171,10 +152,6 @@ __device__ __forceinline__ void umma_commit_both_if(uint32_t issue, uint32_t bar
                :: "r"(bar), "h"((uint16_t)3), "r"(issue) : "memory");
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return (addr & 0x3FFFFu) >> 4; }
-__device__ __forceinline__ void umma_commit_both(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               :: "r"(bar), "h"((uint16_t)3) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
