@@ -126,6 +126,8 @@ class BoundSample:
         L = _lib.lib()
         # kernel choice: tensor-core kernels need the shipped topology and no class output
         want = DEFAULT_TC_PATH if path == "auto" else path
+        if want == "tc3" and path == "auto" and not self.engine.tc3_in_range:
+            want = "tc2"                # this decoder already left the fp8 operand range once: do not try again
         tc2 = tc3 = None
         if want == "tc3":
             tc3 = None if want_cls else self._tc3_for(p_absmax)
@@ -158,6 +160,7 @@ class BoundSample:
                     if path == "tc3" and os.environ.get("ALIGNSDF_B200_STRICT_PATH"):
                         raise AsdfError("k1_tc3: activation outside the fp8 operand range")
                     FALLBACKS["tc3_to_tc2"] += 1
+                    self.engine.tc3_in_range = False
                     return self._run(q, n, want_cls, bbox, "tc2", p_absmax)
             elif use_tc2:
                 rc = L.asdf_tc2_eval(_lib.ptr(self.engine.tc2_static), _lib.ptr(tc2.sample), C.byref(q),
@@ -230,6 +233,7 @@ class DecoderEngine:
         self.tc3_static = None
         self.tc2_scales = None
         self.tc3_scales = None
+        self.tc3_in_range = True        # cleared when a k1_tc3 launch reports an activation >= 448 (sticky)
         self.tc_supported = False
         try:
             from . import tc_pack
