@@ -223,3 +223,19 @@ def test_fast_component_filter_matches_generic_split():
         m = trimesh_lite.largest_watertight_component_mc(pts, f, v, vol.shape, [sp] * 3)
         ev, ef = mo.largest_component_if_split(pts, f)
         assert np.array_equal(m.vertices, ev) and np.array_equal(m.faces, ef)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's torch-CPU path through the oracle port) runs without a GPU
+    and prints one JSON line carrying the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--N", "64"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mq/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == dict(value=line["value"], unit="Mq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
