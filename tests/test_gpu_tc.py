@@ -175,3 +175,22 @@ def test_tc3_falls_back_to_fp16_corrections_when_activations_leave_the_fp8_range
     assert engine.FALLBACKS["tc3_to_tc2"] == before + 1
     hs, os_, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="simt")
     assert (ht - hs).abs().max() <= 1e-5 and (ot - os_).abs().max() <= 1e-5
+
+
+def test_tc3_full_256_grid_within_contract_of_the_fp32_kernel():
+    """BASELINE's full size: all 16.7 M points of the 256^3 pass-1 grid, product kernel (fp16 + fp8 corrections)
+    vs the exact-fp32 generic kernel (itself pinned to the reference's golden fields): <= 1e-5 everywhere, same
+    bounding box, no range fallback."""
+    from alignsdf_b200 import synthetic
+    dec = synthetic.make_decoder(0)
+    s = synthetic.make_sample(0).to(torch.device("cuda"))
+    bound = engine.get_engine(dec, torch.device("cuda")).bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    N = 256
+    before = engine.FALLBACKS["tc3_to_tc2"]
+    ht, ot, _, bt = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="tc3")
+    assert engine.FALLBACKS["tc3_to_tc2"] == before
+    hs, os_, _, bs = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="simt")
+    eh, eo = float((ht - hs).abs().max()), float((ot - os_).abs().max())
+    assert eh <= TOL and eo <= TOL, (eh, eo)
+    assert eh <= 7e-6 and eo <= 7e-6, (eh, eo)        # observed ~3e-6 at this size
+    assert torch.equal(bt, bs)
