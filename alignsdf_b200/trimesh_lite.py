@@ -74,8 +74,8 @@ def export_ply_records(path, vertices, face_records):
               f"element face {len(rec)}\nproperty list uchar int vertex_indices\nend_header\n")
     with open(path, "wb") as fh:
         fh.write(header.encode("ascii"))
-        fh.write(memoryview(v).cast("B"))
-        fh.write(memoryview(rec).cast("B"))
+        fh.write(v)                       # contiguous arrays go out through the buffer protocol, no copy
+        fh.write(rec)
 
 
 def split(mesh: Mesh, only_watertight=True):

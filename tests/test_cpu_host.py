@@ -239,3 +239,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "Mq/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == dict(value=line["value"], unit="Mq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+
+
+def test_ply_writer_from_device_style_face_records(tmp_path):
+    """export_ply_records (face records serialised as uint8 [F,13], what engine.ply_face_records builds on the
+    GPU) writes the same bytes as export_ply."""
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((37, 3)).astype(np.float32)
+    f = rng.integers(0, 37, (55, 3)).astype(np.int32)
+    rec = np.empty((55, 13), np.uint8)
+    rec[:, 0] = 3
+    rec[:, 1:] = f.view(np.uint8).reshape(55, 12)
+    a, b = str(tmp_path / "a.ply"), str(tmp_path / "b.ply")
+    trimesh_lite.export_ply(a, v, f)
+    trimesh_lite.export_ply_records(b, v, rec)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    rv, rf = mo.read_ply(b)
+    assert np.array_equal(rv, v) and np.array_equal(rf, f)
+    trimesh_lite.export_ply_records(b, v[:0], rec[:0])          # empty mesh: header only
+    rv, rf = mo.read_ply(b)
+    assert rv.shape == (0, 3) and rf.shape[0] == 0
