@@ -14,6 +14,8 @@ import torch
 ASDF_MAX_LAYERS = 8
 ASDF_MAX_POINT_DIM = 64
 QUERY_GRID_REFERENCE, QUERY_GRID_REGULAR, QUERY_POINTS = 0, 1, 2
+TC_F16X3, TC_F16_F8 = 0, 1          # asdf_tc_launch.kind
+ABI_VERSION = 2
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalignsdf_b200.so")
 
@@ -36,9 +38,17 @@ class SimtDesc(C.Structure):
                 ("table", ((C.c_int32 * 8) * ASDF_MAX_LAYERS) * 2)]
 
 
-class TcDesc(C.Structure):
-    _fields_ = [("h", C.c_int32 * 2), ("act_scale", C.c_float), ("w_scale", (C.c_float * 3) * 2),
-                ("branch_stride", C.c_int64), ("debug_dev", C.c_void_p)]
+class TcLaunch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_decoders", C.c_int32), ("n_samples", C.c_int32), ("reserved", C.c_int32),
+                ("static_dev", C.c_void_p), ("samples_dev", C.c_void_p), ("sample_stride", C.c_int64),
+                ("grid_dev", C.c_void_p), ("out_hand_dev", C.c_void_p), ("out_obj_dev", C.c_void_p),
+                ("out_stride", C.c_int64), ("bbox_dev", C.c_void_p), ("status_dev", C.c_void_p)]
+
+
+class TcBindDesc(C.Structure):
+    _fields_ = [("n_decoders", C.c_int32), ("latent_size", C.c_int32), ("n_features", C.c_int32 * 2),
+                ("feature_index", (C.c_int32 * ASDF_MAX_POINT_DIM) * 2), ("decoder_stride", C.c_int64),
+                ("act_scale", C.c_float), ("p_absmax", C.c_float), ("w_scale", (C.c_double * 3) * 2)]
 
 
 class McParams(C.Structure):
@@ -64,25 +74,18 @@ def lib():
     L.asdf_last_error.restype = C.c_char_p
     L.asdf_device_ok.restype = C.c_int
     L.asdf_simt_eval.restype = C.c_int
-    L.asdf_simt_eval.argtypes = [C.POINTER(SimtDesc), vp, vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp]
+    L.asdf_simt_eval.argtypes = [C.POINTER(SimtDesc), vp, vp, vp, C.POINTER(Query), vp, vp, i32p, vp, i32p, vp]
     L.asdf_tc_eval.restype = C.c_int
-    L.asdf_tc_eval.argtypes = [C.POINTER(TcDesc), vp, vp, C.POINTER(Query), vp, vp, i32p, vp]
-    L.asdf_tc2_eval.restype = C.c_int
-    L.asdf_tc2_eval.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, vp]
-    L.asdf_tc2_eval_debug.restype = C.c_int
-    L.asdf_tc2_eval_debug.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, vp, vp]
-    L.asdf_tc2_static_bytes.restype = C.c_int64
-    L.asdf_tc2_sample_bytes.restype = C.c_int64
-    L.asdf_tc3_eval.restype = C.c_int
-    L.asdf_tc3_eval.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp]
-    L.asdf_tc3_eval_debug.restype = C.c_int
-    L.asdf_tc3_eval_debug.argtypes = [vp, vp, C.POINTER(Query), vp, vp, i32p, i32p, vp, vp]
-    L.asdf_tc3_static_bytes.restype = C.c_int64
-    L.asdf_tc3_sample_bytes.restype = C.c_int64
-    L.asdf_tc_selftest.restype = C.c_int
-    L.asdf_tc_selftest.argtypes = [vp, vp, vp, vp]
+    L.asdf_tc_eval.argtypes = [C.POINTER(TcLaunch), C.POINTER(Query), vp]
     L.asdf_tc_static_bytes.restype = C.c_int64
-    L.asdf_tc_sample_floats.restype = C.c_int64
+    L.asdf_tc_static_bytes.argtypes = [C.c_int32]
+    L.asdf_tc_sample_bytes.restype = C.c_int64
+    L.asdf_tc_bind.restype = C.c_int
+    L.asdf_tc_bind.argtypes = [C.POINTER(TcBindDesc), vp, vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp]
+    L.asdf_tc_bind_static_doubles.restype = C.c_int64
+    L.asdf_tc_bind_static_doubles.argtypes = [C.c_int32, C.c_int32]
+    L.asdf_regrid.restype = C.c_int
+    L.asdf_regrid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp]
     L.asdf_grid_points.restype = C.c_int
     L.asdf_grid_points.argtypes = [C.POINTER(Query), vp, vp]
     L.asdf_nerf_embed.restype = C.c_int
@@ -103,7 +106,7 @@ def lib():
     L.asdf_cc_mark.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]
     L.asdf_cc_gather.restype = C.c_int
     L.asdf_cc_gather.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
-    if L.asdf_abi_version() != 1:
+    if L.asdf_abi_version() != ABI_VERSION:
         raise AsdfError("ABI version mismatch between alignsdf_b200 and its shared library")
     _lib = L
     return L

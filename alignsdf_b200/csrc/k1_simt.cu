@@ -27,6 +27,7 @@ struct SimtArgs {
   float* out_hand;
   float* out_obj;
   int32_t* out_cls;
+  float* out_logits;
   int32_t* bbox;
 };
 
@@ -239,8 +240,12 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
         if (threadIdx.x < PT) {
           int best = 0;
           float bv = res[threadIdx.x] + __ldg(a.cls + t[0]);
+          const int64_t ip = base + threadIdx.x;
+          float* lg = (a.out_logits && ip < q.end) ? a.out_logits + (size_t)(ip - q.begin) * d.n_class : nullptr;
+          if (lg) lg[0] = bv;
           for (int c = 1; c < d.n_class; ++c) {
             const float v = res[c * PT + threadIdx.x] + __ldg(a.cls + (size_t)c * (t[0] + 1) + t[0]);
+            if (lg) lg[c] = v;
             if (v > bv) { bv = v; best = c; }
           }
           cls_s[threadIdx.x] = best;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
 extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev,
                               const float* sample_dev, const float* cls_dev, const asdf_query* q,
                               float* out_hand_dev, float* out_obj_dev, int32_t* out_cls_dev,
-                              int32_t* bbox_dev, void* stream) {
+                              float* out_logits_dev, int32_t* bbox_dev, void* stream) {
   using namespace asdf;
   ASDF_REQUIRE(desc && q && static_dev && sample_dev && out_hand_dev, "asdf_simt_eval: null argument");
   ASDF_REQUIRE(desc->n_branches == 1 || desc->n_branches == 2, "n_branches must be 1 or 2");
@@ -319,13 +324,9 @@ extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_de
   if (q->end == q->begin) return ASDF_OK;
   SimtArgs a;
   a.d = *desc; a.q = *q; a.stat = static_dev; a.samp = sample_dev; a.cls = cls_dev;
-  a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.out_cls = out_cls_dev; a.bbox = bbox_dev;
+  a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.out_cls = out_cls_dev; a.out_logits = out_logits_dev; a.bbox = bbox_dev;
   const size_t smem = (size_t)(2 * MAXW * PTS + ASDF_MAX_POINT_DIM * PTS + 8 * PT + 2 * PT + PT) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    ASDF_CUDA_CHECK(cudaFuncSetAttribute(simt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  ASDF_CUDA_CHECK(cudaFuncSetAttribute(simt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   ASDF_CUDA_CHECK(cudaGetDevice(&dev));
   ASDF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

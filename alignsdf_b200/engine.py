@@ -17,10 +17,18 @@ from . import _lib, packer
 from ._lib import AsdfError
 
 INT_MAX = 2 ** 31 - 1
-# which tensor-core kernel "auto" prefers: "tc3" = k1_tc3.cu (fp16 + fp8 corrections, falls back to
-# "tc2" = k1_tc2.cu (fp16 x3) when an activation leaves the fp8 operand range), "tc" = k1_tc.cu
-DEFAULT_TC_PATH = "tc3"
-FALLBACKS = {"tc3_to_tc2": 0}    # launches whose fp8 range flag fired and were re-run through k1_tc2.cu
+F16X3, F16_F8 = _lib.TC_F16X3, _lib.TC_F16_F8
+KIND_NAMES = {F16X3: "f16x3", F16_F8: "f16+2xe4m3"}
+# ALIGNSDF_B200_PATH: "auto" (default), "f16" (k1_tc F16X3), "f8" (k1_tc F16_F8, no calibration), "simt" (k1_simt)
+_PATH_ALIASES = {"tc2": "f16", "tc3": "f8", "tc": "f16"}
+# "auto" on the shipped topology: the F16_F8 kind (2/3 of the tensor time) is used only for samples whose
+# calibration run -- both kinds on CALIB_POINTS random points of the cube, compared on the device -- agrees
+# to CALIB_TOL; F16X3 itself stays within ~2.5e-6 x output range of the reference (tests), so an accepted
+# sample is inside the 1e-5 contract with margin.  A rejection is sticky per decoder.
+CALIB_POINTS = 16384
+CALIB_TOL = 2.5e-6
+STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0, "simt_launches": 0}
+FALLBACKS = STATS                # old name
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
@@ -37,35 +45,62 @@ def _device_of(latent, device=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-class BoundSample:
-    """A decoder with one sample's latent/pose folded in, ready to be queried."""
+def new_bbox(device, n=1):
+    """int32[n,12] bounding boxes in their initial state ({INT_MAX x3, -1 x3} per branch)."""
+    return torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3, dtype=torch.int32,
+                        device=device).repeat(n, 1)
 
-    def __init__(self, engine, branches, feature_mode, nerf_freqs=0):
+
+def make_query(mode, N=0, begin=0, end=0, voxel=0.0, origin=(0.0, 0.0, 0.0), points=None, bbox_mask=0):
+    q = _lib.Query()
+    q.mode, q.N, q.begin, q.end = mode, int(N), int(begin), int(end)
+    q.voxel = float(voxel)
+    for k in range(3):
+        q.origin[k] = float(origin[k])
+    if points is None:
+        q.points_dev, q.point_stride = None, 0
+    else:
+        q.points_dev, q.point_stride = points.data_ptr(), int(points.shape[1])
+    q.bbox_mask = int(bbox_mask)
+    return q
+
+
+class BoundSample:
+    """S samples (latent + pose each) bound to one decoder, ready to be queried -- S = 1 for the drop-in calls.
+
+    Tensor-core path: the per-sample blocks are built ON THE DEVICE (asdf_tc_bind) from the latents and the
+    pose-align affine maps; the host only inverts the 17 rigid 4x4 transforms of a sample.  The generic fp32
+    kernel (any topology, feature queries, NeRF encoding, class output) folds on the host, lazily."""
+
+    def __init__(self, engine, inputs, feature_mode, nerf_freqs=0):
         self.engine = engine
+        self.inputs = inputs                    # [(latent, specs, mano_results, obj_results)]
+        self.S = len(inputs)
         self.feature_mode = feature_mode
         self.nerf_freqs = int(nerf_freqs)       # > 0: xyz queries, NeRF-encoded inside the generic kernel
         self.device = engine.device
-        self._simt_ready = False
-        self._two_outputs = len(branches) == 2 or int(branches[0].layers[-1].B.shape[0]) == 2
-        self.tc = None
-        self.tc2 = None
-        self.tc3 = None
-        self._branches = branches
-        if not feature_mode and not self.nerf_freqs and engine.tc_supported:
-            from . import tc_pack
-            self.tc = tc_pack.bind(engine, branches)
+        self.tc_ok = engine.tc_supported and not feature_mode and not self.nerf_freqs
+        self._two_outputs = engine.n_outputs == 2
+        self._simt = {}                         # sample index -> (pack, sample tensor, desc)
+        self._tc_inputs = None
+        self._tc_blocks = {}                    # kind -> (blocks, p_absmax, bind status)
+        self._calib = None                      # device f32 scalar: max |F16_F8 - F16X3| on the calibration points
+        self._calib_checked = False
+        self._pending = []                      # (kind, status word, bind status) of launches not yet checked by verify()
+        self.kinds_used = set()
 
-    def _ensure_simt(self):
-        """Buffers + descriptor of the generic fp32 kernel, built on first use (the tensor-core paths
-        never need them)."""
-        if self._simt_ready:
-            return
+    # ------------------------------------------------------------------ generic fp32 kernel
+    def _ensure_simt(self, i=0):
+        """Buffers + descriptor of the generic fp32 kernel for sample i, built on first use."""
+        if i in self._simt:
+            return self._simt[i]
         engine, topo, dev = self.engine, self.engine.topo, self.device
-        pack = packer.pack_simt(self._branches)
-        self.simt_pack = pack
+        latent, specs, mano, obj = self.inputs[i]
+        branches = packer.fold_decoder(topo, latent, specs, mano, obj, self.feature_mode)
+        pack = packer.pack_simt(branches)
         if engine.simt_static is None:      # static weights do not depend on the sample
             engine.simt_static = torch.from_numpy(pack.static).to(dev)
-        self.simt_sample = torch.from_numpy(pack.sample).to(dev, non_blocking=True)
+        sample = torch.from_numpy(pack.sample).to(dev, non_blocking=True)
         d = _lib.SimtDesc()
         d.n_branches, d.n_layers, d.n_outputs = pack.n_branches, pack.n_layers, pack.n_outputs
         d.pre_tanh = int(topo.pre_tanh)
@@ -80,107 +115,192 @@ class BoundSample:
             for l in range(pack.n_layers):
                 for k in range(8):
                     d.table[b][l][k] = int(pack.table[b, l, k])
-        self.simt_desc = d
-        self._simt_ready = True
+        self._simt[i] = (pack, sample, d)
+        return self._simt[i]
 
-    def _tc2_for(self, p_absmax: float):
-        """Per-sample block of the v2 tensor-core kernel, valid for |xyz| <= p_absmax (the point
-        operand scale is baked into it); returns None when the fp16 ranges cannot be met."""
-        if self.feature_mode or self.nerf_freqs or not self.engine.tc_supported:
-            return None
-        need = max(2.0, float(p_absmax) * 1.01)
-        if self.tc2 is None or self.tc2.info["p_absmax"] < need:
-            from . import tc2_pack
-            try:
-                self.tc2 = tc2_pack.bind(self.engine, self._branches, need)
-            except ValueError:
-                return None
-        return self.tc2
-
-    def _tc3_for(self, p_absmax: float):
-        """Same for the v3 kernel (its own block: activations are not pre-scaled there)."""
-        if self.feature_mode or self.nerf_freqs or not self.engine.tc_supported:
-            return None
-        need = max(2.0, float(p_absmax) * 1.01)
-        if self.tc3 is None or self.tc3.info["p_absmax"] < need:
-            from . import tc3_pack
-            try:
-                self.tc3 = tc3_pack.bind(self.engine, self._branches, need)
-            except ValueError:
-                return None
-        return self.tc3
-
-    # ------------------------------------------------------------------
-    def _run(self, q: _lib.Query, n: int, want_cls: bool, bbox: bool, path: str, p_absmax: float = 2.0):
+    def _launch_simt(self, q, n, want_cls, box, i=0, want_logits=False):
         dev = self.device
+        _, sample, desc = self._ensure_simt(i)
         hand = torch.empty(n, dtype=torch.float32, device=dev)
-        two = self._two_outputs
-        obj = torch.empty(n, dtype=torch.float32, device=dev) if two else None
+        obj = torch.empty(n, dtype=torch.float32, device=dev) if self._two_outputs else None
         cls = torch.empty(n, dtype=torch.int32, device=dev) if want_cls else None
-        box = None
-        if bbox:
-            box = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3,
-                               dtype=torch.int32, device=dev)
-        if n == 0:                      # empty query: nothing to launch
-            return hand, obj, cls, box
-        L = _lib.lib()
-        # kernel choice: tensor-core kernels need the shipped topology and no class output
-        want = DEFAULT_TC_PATH if path == "auto" else path
-        if want == "tc3" and path == "auto" and not self.engine.tc3_in_range:
-            want = "tc2"                # this decoder already left the fp8 operand range once: do not try again
-        tc2 = tc3 = None
-        if want == "tc3":
-            tc3 = None if want_cls else self._tc3_for(p_absmax)
-            if tc3 is None:
-                if path == "tc3":
-                    raise AsdfError("tensor-core (v3) path requested but not available for this decoder/query")
-                want = "tc2"
-        if want == "tc2":
-            tc2 = None if want_cls else self._tc2_for(p_absmax)
-            if tc2 is None:
-                if path == "tc2":
-                    raise AsdfError("tensor-core (v2) path requested but not available for this decoder/query")
-                want = "tc"
-        if want == "tc" and (self.tc is None or want_cls):
-            if path == "tc":
-                raise AsdfError("tensor-core path requested but not available for this decoder/query")
-            want = "simt"
-        use_tc3, use_tc2, use_tc = want == "tc3", want == "tc2", want == "tc"
+        logits = None
+        if want_logits and desc.n_class > 0:
+            logits = torch.empty((n, desc.n_class), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            st = _lib.stream_ptr(dev)
-            if use_tc3:
-                status = torch.zeros(1, dtype=torch.int32, device=dev)
-                rc = L.asdf_tc3_eval(_lib.ptr(self.engine.tc3_static), _lib.ptr(tc3.sample), C.byref(q),
-                                     _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(box), _lib.ptr(status), st)
-                _lib.check(rc, "asdf_tc3_eval")
-                LAUNCHES["count"] += 1
-                if int(status.item()) != 0:
-                    # an activation left the range of the fp8 correction operands: the launch's outputs
-                    # (and bbox) are not trustworthy -> same query through the all-fp16 kernel
-                    if path == "tc3" and os.environ.get("ALIGNSDF_B200_STRICT_PATH"):
-                        raise AsdfError("k1_tc3: activation outside the fp8 operand range")
-                    FALLBACKS["tc3_to_tc2"] += 1
-                    self.engine.tc3_in_range = False
-                    return self._run(q, n, want_cls, bbox, "tc2", p_absmax)
-            elif use_tc2:
-                rc = L.asdf_tc2_eval(_lib.ptr(self.engine.tc2_static), _lib.ptr(tc2.sample), C.byref(q),
-                                     _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(box), st)
-                _lib.check(rc, "asdf_tc2_eval")
-                LAUNCHES["count"] += 1
-            elif use_tc:
-                rc = L.asdf_tc_eval(C.byref(self.tc.desc), _lib.ptr(self.engine.tc_static),
-                                    _lib.ptr(self.tc.sample), C.byref(q), _lib.ptr(hand),
-                                    _lib.ptr(obj), _lib.ptr(box), st)
-                _lib.check(rc, "asdf_tc_eval")
-                LAUNCHES["count"] += 1
-            else:
-                self._ensure_simt()
-                rc = L.asdf_simt_eval(C.byref(self.simt_desc), _lib.ptr(self.engine.simt_static),
-                                      _lib.ptr(self.simt_sample), _lib.ptr(self.engine.cls_dev),
-                                      C.byref(q), _lib.ptr(hand), _lib.ptr(obj), _lib.ptr(cls),
-                                      _lib.ptr(box), st)
-                _lib.check(rc, "asdf_simt_eval")
-                LAUNCHES["count"] += 1
+            rc = _lib.lib().asdf_simt_eval(C.byref(desc), _lib.ptr(self.engine.simt_static), _lib.ptr(sample),
+                                           _lib.ptr(self.engine.cls_dev), C.byref(q), _lib.ptr(hand), _lib.ptr(obj),
+                                           _lib.ptr(cls), _lib.ptr(logits), _lib.ptr(box), _lib.stream_ptr(dev))
+        _lib.check(rc, "asdf_simt_eval")
+        LAUNCHES["count"] += 1
+        STATS["simt_launches"] += 1
+        self.kinds_used.add("simt")
+        return hand, obj, cls, logits
+
+    # ------------------------------------------------------------------ tensor-core kernel
+    def _ensure_tc_inputs(self):
+        if self._tc_inputs is None:
+            dev, topo = self.device, self.engine.topo
+            lat = torch.stack([torch.as_tensor(inp[0]).detach().reshape(-1).to(torch.float32) for inp in self.inputs])
+            if lat.shape[1] != topo.latent_size:
+                raise ValueError(f"latent has {lat.shape[1]} entries, decoder expects {topo.latent_size} "
+                                 "(per-point PixelAlign latents are not folded)")
+            aff = np.zeros((self.S, _lib.ASDF_MAX_POINT_DIM, 4))
+            for i, (_, specs, mano, obj) in enumerate(self.inputs):
+                if specs.get("PixelAlign", False):
+                    raise AsdfError("PixelAlign samples are evaluated by alignsdf_b200.pixel_align, not folded")
+                A, c = packer.embedding_affine(specs, mano, obj)
+                aff[i, :A.shape[0], :3], aff[i, :A.shape[0], 3] = A, c
+            self._tc_inputs = (lat.to(dev, non_blocking=True).contiguous(),
+                               torch.from_numpy(aff).to(dev, non_blocking=True))
+        return self._tc_inputs
+
+    def tc_blocks(self, kind, p_absmax=2.0):
+        """Per-sample P-tile blocks of `kind`, valid for |xyz| <= p_absmax (the point-operand scale is baked in);
+        built by asdf_tc_bind on the device, asynchronously.  -> (uint8 [S, bytes], bind status int32[1])."""
+        need = max(2.0, float(p_absmax) * 1.01)
+        hit = self._tc_blocks.get(kind)
+        if hit is not None and hit[1] >= need:
+            return hit[0], hit[2]
+        eng, dev = self.engine, self.device
+        lat, aff = self._ensure_tc_inputs()
+        L = _lib.lib()
+        nbytes = int(L.asdf_tc_sample_bytes())
+        blocks = torch.zeros((self.S, nbytes), dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        fold = torch.empty(self.S * eng.n_dec * 2 * 512 * 4, dtype=torch.float64, device=dev)
+        desc = eng.bind_desc(kind, need)
+        with torch.cuda.device(dev):
+            rc = L.asdf_tc_bind(C.byref(desc), _lib.ptr(eng.bind_static()), _lib.ptr(lat), _lib.ptr(aff), self.S,
+                                _lib.ptr(fold), _lib.ptr(blocks), nbytes, _lib.ptr(status), _lib.stream_ptr(dev))
+        _lib.check(rc, "asdf_tc_bind")
+        LAUNCHES["count"] += 2
+        self._tc_blocks[kind] = (blocks, need, status)
+        return blocks, status
+
+    def launch_tc(self, kind, q, n, store=True, box=None, grid=None, p_absmax=2.0):
+        """One asdf_tc_eval over all S samples (asynchronous, no host sync).
+        -> (hand [S,n] | None, obj [S,n] | None, status int32[1]: bit 0 range flag, bit 1 bind failure)."""
+        eng, dev = self.engine, self.device
+        blocks, bind_status = self.tc_blocks(kind, p_absmax)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pending.append((kind, status, bind_status))
+        hand = torch.empty((self.S, n), dtype=torch.float32, device=dev) if store else None
+        obj = torch.empty((self.S, n), dtype=torch.float32, device=dev) if store else None
+        l = _lib.TcLaunch()
+        l.kind, l.n_decoders, l.n_samples = kind, eng.n_dec, self.S
+        l.static_dev = eng.tc_static(kind).data_ptr()
+        l.samples_dev, l.sample_stride = blocks.data_ptr(), blocks.shape[1]
+        l.grid_dev = None if grid is None else grid.data_ptr()
+        l.out_hand_dev = None if hand is None else hand.data_ptr()
+        l.out_obj_dev = None if obj is None else obj.data_ptr()
+        l.out_stride = n
+        l.bbox_dev = None if box is None else box.data_ptr()
+        l.status_dev = status.data_ptr()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().asdf_tc_eval(C.byref(l), C.byref(q), _lib.stream_ptr(dev))
+        _lib.check(rc, "asdf_tc_eval")
+        LAUNCHES["count"] += 1
+        STATS["f8_launches" if kind == F16_F8 else "f16_launches"] += 1
+        self.kinds_used.add(KIND_NAMES[kind])
+        return hand, obj, status
+
+    def _calibrate(self):
+        """Launch (once per bound batch, asynchronously) both kinds on the calibration points."""
+        if self._calib is None:
+            pts = self.engine.calib_points()
+            q = make_query(_lib.QUERY_POINTS, end=pts.shape[0], points=pts)
+            h8, o8, _ = self.launch_tc(F16_F8, q, pts.shape[0])
+            h16, o16, _ = self.launch_tc(F16X3, q, pts.shape[0])
+            self._calib = torch.maximum((h8 - h16).abs().max(), (o8 - o16).abs().max())
+        return self._calib
+
+    def auto_kind(self, path=None):
+        """Kind the next tensor-core launch of this batch should use; with "auto" the F16_F8 kind is speculative
+        until verify() has looked at the calibration result."""
+        path = path or self.engine.path
+        if path == "f16":
+            return F16X3
+        if path == "f8":
+            return F16_F8
+        if self.engine.f8_ok is False:
+            return F16X3
+        self._calibrate()
+        return F16_F8
+
+    def verify(self):
+        """Host check (one small D2H, synchronises) of everything launched since the last call.
+        -> "ok" | "f16" (re-run through F16X3: calibration or fp8 operand range rejected) | "simt" (fp16
+        operands out of range or bind failure: re-run through the generic kernel)."""
+        pending, self._pending = self._pending, []
+        check_calib = self._calib is not None and not self._calib_checked
+        if not pending and not check_calib:
+            return "ok"
+        words = [(st | bst).reshape(()).to(torch.float32) for _, st, bst in pending]
+        if check_calib:
+            words.append(self._calib.reshape(()))
+        vals = torch.stack(words).cpu().tolist()
+        eng, verdict = self.engine, "ok"
+        if check_calib:
+            self._calib_checked = True
+            err = vals.pop()
+            eng.calib.update(err=max(err, eng.calib.get("err") or 0.0), samples=eng.calib.get("samples", 0) + self.S)
+            if not err <= CALIB_TOL:            # also catches NaN
+                if eng.f8_ok is not False:
+                    STATS["f8_rejected"] += 1
+                eng.f8_ok = False
+                if any(k == F16_F8 for k, _, _ in pending):
+                    verdict = "f16"
+            elif eng.f8_ok is None:
+                eng.f8_ok = True
+        for (k, _, _), v in zip(pending, vals):
+            if int(v) == 0:
+                continue
+            if k == F16_F8 and not (int(v) & 2):
+                if eng.f8_ok is not False:
+                    STATS["f8_rejected"] += 1
+                eng.f8_ok = False
+                if verdict == "ok":
+                    verdict = "f16"
+            else:                               # F16X3 range flag or a bind failure: only the generic kernel is left
+                STATS["tc_to_simt"] += 1
+                self.tc_ok = False
+                verdict = "simt"
+        return verdict
+
+    # ------------------------------------------------------------------ single-sample calls (drop-in API)
+    def _run(self, q, n, want_cls, bbox, path, p_absmax=2.0, want_logits=False):
+        assert self.S == 1, "single-sample call on a batch"
+        dev = self.device
+        box = new_bbox(dev)[0] if bbox else None
+        if n == 0:                      # empty query: nothing to launch
+            e = torch.empty(0, dtype=torch.float32, device=dev)
+            return e, (e.clone() if self._two_outputs else None), \
+                (torch.empty(0, dtype=torch.int32, device=dev) if want_cls else None), box
+        path = _PATH_ALIASES.get(path, path)
+        use_tc = self.tc_ok and not want_cls and not want_logits and path != "simt"
+        if path in ("f16", "f8") and not use_tc:
+            raise AsdfError("tensor-core path requested but not available for this decoder/query")
+        while use_tc:
+            kind = self.auto_kind(path)
+            if box is not None:
+                box.copy_(new_bbox(dev)[0])
+            hand, obj, _ = self.launch_tc(kind, q, n, True, box, None, p_absmax)
+            v = self.verify()
+            if v == "ok":
+                return hand[0], obj[0], None, box
+            if v == "f16":              # same query through F16X3 ("auto" now answers F16X3 by itself)
+                if path == "f8":
+                    if os.environ.get("ALIGNSDF_B200_STRICT_PATH"):
+                        raise AsdfError("k1_tc F16_F8: activation outside the fp8 operand range")
+                    path = "f16"
+                continue
+            use_tc = False              # "simt"
+        if box is not None:
+            box.copy_(new_bbox(dev)[0])
+        hand, obj, cls, logits = self._launch_simt(q, n, want_cls, box, 0, want_logits)
+        if want_logits:
+            return hand, obj, (cls, logits), box
         return hand, obj, cls, box
 
     def eval_grid(self, N, voxel, origin, mode="reference", begin=0, end=None, bbox_mask=0,
@@ -189,36 +309,52 @@ class BoundSample:
         if self.feature_mode and not self.nerf_freqs:
             raise AsdfError("grid evaluation needs an xyz-folded sample (feature_mode=False)")
         end = N ** 3 if end is None else end
-        q = _lib.Query()
-        q.mode, q.N, q.begin, q.end = _GRID_MODES[mode], int(N), int(begin), int(end)
-        q.voxel = float(voxel)
-        for k in range(3):
-            q.origin[k] = float(origin[k])
-        q.points_dev, q.point_stride, q.bbox_mask = None, 0, int(bbox_mask)
+        q = make_query(_GRID_MODES[mode], N, begin, end, voxel, origin, bbox_mask=bbox_mask)
         # bound on |xyz| over the (possibly sheared: up to one extra voxel) lattice
         pmax = max(max(abs(float(origin[k])), abs(float(origin[k]) + (N + 1) * float(voxel))) for k in range(3))
         return self._run(q, end - begin, want_cls, bbox_mask != 0, path or self.engine.path, pmax)
 
-    def eval_points(self, points: torch.Tensor, want_cls=False, path=None):
+    def eval_points(self, points: torch.Tensor, want_cls=False, path=None, want_logits=False):
         """points: CUDA f32 [P, stride]; xyz rows, or embedded feature rows in feature mode."""
         _lib.require_cuda(points, "points")
         pts = points.to(torch.float32).contiguous()
-        q = _lib.Query()
-        q.mode, q.N, q.begin, q.end = _lib.QUERY_POINTS, 0, 0, int(pts.shape[0])
-        q.voxel = 0.0
-        q.points_dev, q.point_stride, q.bbox_mask = pts.data_ptr(), int(pts.shape[1]), 0
+        q = make_query(_lib.QUERY_POINTS, end=pts.shape[0], points=pts)
         pth = path or self.engine.path
         pmax = 2.0
-        if pts.shape[0] and not self.feature_mode and pth in ("auto", "tc2", "tc3") and self.engine.tc_supported:
+        if pts.shape[0] and self.tc_ok and not want_cls and not want_logits and pth != "simt":
             pmax = float(pts[:, :3].abs().max())
-        hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, pth, pmax)
+        hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, pth, pmax, want_logits)
         return hand, obj, cls
+
+    # ------------------------------------------------------------------ the two grid passes of a batch, no host sync
+    def two_pass(self, N, bbox_mask, mode="reference", kind=None, keep_pass1=False):
+        """utils/mesh.py:24-120 for all S samples: pass 1 over [-1,1]^3 (bounding boxes only unless
+        ``keep_pass1``), asdf_regrid on the device, pass 2 on the per-sample lattices.  Nothing here waits for
+        the GPU; call verify() once the results are needed.
+        -> dict(hand [S,N^3], obj [S,N^3], grid [S,4] = voxel, origin, minmax [S,6], box [S,12], pass1_*)."""
+        dev = self.device
+        kind = self.auto_kind() if kind is None else kind
+        n = N ** 3
+        voxel = 2.0 / (N - 1)
+        q1 = make_query(_GRID_MODES[mode], N, 0, n, voxel, (-1.0, -1.0, -1.0), bbox_mask=bbox_mask)
+        box = new_bbox(dev, self.S)
+        p1h, p1o, _ = self.launch_tc(kind, q1, n, keep_pass1, box)
+        grid = torch.empty((self.S, 4), dtype=torch.float32, device=dev)
+        minmax = torch.empty((self.S, 6), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().asdf_regrid(_lib.ptr(box), self.S, int(bbox_mask), N, float(np.float32(voxel)),
+                                              _lib.ptr(grid), _lib.ptr(minmax), _lib.stream_ptr(dev)), "asdf_regrid")
+        LAUNCHES["count"] += 1
+        q2 = make_query(_GRID_MODES[mode], N, 0, n, 0.0, (0.0, 0.0, 0.0))
+        hand, obj, _ = self.launch_tc(kind, q2, n, True, None, grid)
+        return dict(hand=hand, obj=obj, grid=grid, minmax=minmax, box=box, pass1_hand=p1h, pass1_obj=p1o, kind=kind)
 
 
 class DecoderEngine:
     """Per-decoder state: topology, static weights resident in HBM."""
 
     def __init__(self, decoder, device):
+        from . import tc_pack
         self.device = torch.device(device)
         self.topo = packer.decoder_topology(decoder)
         self.simt_static = None
@@ -227,33 +363,69 @@ class DecoderEngine:
             Wc, bc = self.topo.classifier
             self.cls_dev = torch.from_numpy(
                 np.concatenate([Wc, bc[:, None]], 1).astype(np.float32)).to(self.device)
-        self.path = os.environ.get("ALIGNSDF_B200_PATH", "auto")
-        self.tc_static = None
-        self.tc2_static = None
-        self.tc3_static = None
-        self.tc2_scales = None
-        self.tc3_scales = None
-        self.tc3_in_range = True        # cleared when a k1_tc3 launch reports an activation >= 448 (sticky)
-        self.tc_supported = False
-        try:
+        p = os.environ.get("ALIGNSDF_B200_PATH", "auto")
+        self.path = _PATH_ALIASES.get(p, p)
+        if self.path not in ("auto", "f16", "f8", "simt"):
+            raise AsdfError(f"ALIGNSDF_B200_PATH={p!r}: expected auto, f16, f8 or simt")
+        self.n_dec = len(self.topo.branches)
+        last = self.topo.layers[self.topo.branches[0][1]][-1][0]
+        self.n_outputs = 2 if self.n_dec == 2 else int(last.shape[0])
+        self.tc_supported = tc_pack.supported(self.topo)
+        self.w_scale = tc_pack.weight_scales(self.topo) if self.tc_supported else None
+        self._tc_static = {}
+        self._bind_static = None
+        self._calib_points = None
+        self.f8_ok = None               # None: no sample calibrated yet, True: accepted so far, False: rejected (sticky)
+        self.calib = dict(err=None, tol=CALIB_TOL, points=CALIB_POINTS, samples=0)
+
+    def tc_static(self, kind):
+        """Packed weight stream of `kind`, resident in HBM (built on first use)."""
+        if kind not in self._tc_static:
             from . import tc_pack
-            self.tc_supported = tc_pack.supported(self.topo) and _lib.lib().asdf_tc_static_bytes() > 0
-            if self.tc_supported:
-                self.tc_static = tc_pack.pack_static(self)
-                from . import tc2_pack
-                self.tc2_static = tc2_pack.pack_static(self)
-                from . import tc3_pack
-                self.tc3_static = tc3_pack.pack_static(self)
-        except ImportError:
-            self.tc_supported = False
+            self._tc_static[kind] = tc_pack.pack_static(self.topo, kind, self.device)
+        return self._tc_static[kind]
+
+    def bind_static(self):
+        if self._bind_static is None:
+            from . import tc_pack
+            arr = tc_pack.bind_static_numpy(self.topo)
+            assert arr.size == _lib.lib().asdf_tc_bind_static_doubles(self.n_dec, self.topo.latent_size)
+            self._bind_static = torch.from_numpy(arr).to(self.device)
+        return self._bind_static
+
+    def bind_desc(self, kind, p_absmax):
+        from . import tc_pack
+        d = _lib.TcBindDesc()
+        d.n_decoders, d.latent_size = self.n_dec, self.topo.latent_size
+        for b, (tag, _) in enumerate(self.topo.branches):
+            idx = packer.branch_feature_index(self.topo, tag)
+            d.n_features[b] = len(idx)
+            for f, v in enumerate(idx):
+                d.feature_index[b][f] = int(v)
+            for l in range(3):
+                d.w_scale[b][l] = float(self.w_scale[b][l])
+        d.decoder_stride = _lib.lib().asdf_tc_bind_static_doubles(1, self.topo.latent_size)
+        d.act_scale = tc_pack.ACT_SCALE[kind]
+        d.p_absmax = float(p_absmax)
+        return d
+
+    def calib_points(self):
+        """Fixed (seeded) uniform points of [-1,1]^3 the two tensor-core kinds are compared on."""
+        if self._calib_points is None:
+            g = torch.Generator(device="cpu")
+            g.manual_seed(20221017)
+            self._calib_points = (torch.rand(CALIB_POINTS, 3, generator=g) * 2.0 - 1.0).to(self.device)
+        return self._calib_points
 
     def bind(self, latent, specs, mano_results, obj_results, feature_mode=False) -> BoundSample:
+        return self.bind_batch([(latent, specs, mano_results, obj_results)], feature_mode)
+
+    def bind_batch(self, inputs, feature_mode=False) -> BoundSample:
+        """inputs: [(latent, specs, mano_results, obj_results)] of S samples sharing the embedding configuration."""
         # NeRF positional encoding (utils/mesh.py:54-55) is not affine in xyz: the weights are folded as
         # for feature queries and the generic kernel encodes xyz itself
-        nerf = 0 if feature_mode else packer.nerf_freqs(specs, mano_results)
-        branches = packer.fold_decoder(self.topo, latent, specs, mano_results, obj_results,
-                                       feature_mode or nerf > 0)
-        return BoundSample(self, branches, feature_mode or nerf > 0, nerf)
+        nerf = 0 if feature_mode else packer.nerf_freqs(inputs[0][1], inputs[0][2])
+        return BoundSample(self, list(inputs), feature_mode or nerf > 0, nerf)
 
 
 def unwrap_decoder(decoder):

@@ -138,12 +138,29 @@ def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_fi
     np.savez(npz_filename_out, points=pts, labels=labels)
 
 
+def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None):
+    """bound.two_pass + the host check of its speculative parts; re-runs through the next safer kernel kind when
+    the calibration / operand-range flags say so.  -> result dict, or None when only the generic kernel is left."""
+    path = _engine._PATH_ALIASES.get(path, path) if path else bound.engine.path
+    while bound.tc_ok and path != "simt":
+        kind = bound.auto_kind(path)
+        r = bound.two_pass(N, mask, grid_mode, kind, keep_pass1)
+        v = bound.verify()
+        if v == "ok":
+            return r
+        if v == "f16" and path == "f8":
+            path = "f16"
+    return None
+
+
 def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
-                obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None, bound=None):
+                obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None, bound=None,
+                keep_pass1=True):
     """The two evaluation passes of utils/mesh.py:24-120 on the GPU.
 
     Returns dict(pass1_hand, pass1_obj, hand, obj, cls, voxel (0-dim f32 tensor),
-    origin (f32[3] tensor), bound) with [N,N,N] CUDA volumes."""
+    origin (f32[3] tensor), bound) with [N,N,N] CUDA volumes (pass-1 volumes only with ``keep_pass1``:
+    the reference uses them for nothing but the bounding box)."""
     dev = _engine._device_of(latent_vec, device)
     eng = _engine.get_engine(decoder, dev)
     if bound is None:                    # ``bound``: a sample already bound by the caller (pipelined batches)
@@ -152,13 +169,24 @@ def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_b
     mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
     if mask == 0:
         raise ValueError("at least one of hand_branch / obj_branch must be set")
+    shp = (N, N, N)
+    want_cls = cls_branch and eng.topo.classifier is not None
+    if bound.tc_ok and not want_cls:
+        # tensor-core kernel: pass 1 -> asdf_regrid -> pass 2 without a host round trip in between
+        r = _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path)
+        if r is not None:
+            g = r["grid"][0].cpu()
+            mm = r["minmax"][0].cpu()
+            view = lambda t: None if t is None else t[0].view(shp)
+            return dict(pass1_hand=view(r["pass1_hand"]), pass1_obj=view(r["pass1_obj"]), hand=view(r["hand"]),
+                        obj=view(r["obj"]), cls=None, voxel=g[0].clone(), origin=g[1:4].clone(),
+                        min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
     h1, o1, _, box = bound.eval_grid(N, voxel_size, [-1.0, -1.0, -1.0], grid_mode, bbox_mask=mask,
                                      path=path)
     mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
     new_voxel_size, new_origin = _regrid(mn, mx, N, voxel_size)
     h2, o2, c2, _ = bound.eval_grid(N, float(new_voxel_size), new_origin.tolist(), grid_mode,
-                                    want_cls=cls_branch and eng.topo.classifier is not None, path=path)
-    shp = (N, N, N)
+                                    want_cls=want_cls, path=path)
     return dict(pass1_hand=h1.view(shp), pass1_obj=None if o1 is None else o1.view(shp),
                 hand=h2.view(shp), obj=None if o2 is None else o2.view(shp),
                 cls=None if c2 is None else c2.view(shp), voxel=new_voxel_size, origin=new_origin,
@@ -176,7 +204,7 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
     ply_filename_obj = filename + "_obj"
     decoder.eval()
     vols = sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch,
-                       obj_branch, cls_branch, None if device == "cpu" else device, grid_mode)
+                       obj_branch, cls_branch, None if device == "cpu" else device, grid_mode, keep_pass1=False)
     voxel_size = vols["voxel"]
     voxel_origin = vols["origin"].tolist()
     result = {"hand": None, "obj": None}
@@ -269,7 +297,8 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
             mano = None if smp.mano_results is None else {k: to(v) for k, v in smp.mano_results.items()}
             obj = None if smp.obj_results is None else {k: to(v) for k, v in smp.obj_results.items()}
             bound = _engine.get_engine(decoder, dev).bind(latent, smp.specs, mano, obj)
-            bound._tc3_for(2.0)                      # pre-pack the tensor-core block for the unit cube
+            if bound.tc_ok:
+                bound.tc_blocks(bound.auto_kind(), 2.0)      # P tiles built on the device, ahead of the sample's turn
             ready = torch.cuda.Event()
             ready.record(bind_stream[dev])
         return dev, latent, mano, obj, bound, ready

@@ -113,9 +113,37 @@ def _fill_linear(g, mod, hidden_gain):
         mod.bias.copy_(b)
 
 
+def _fill_default(g, mod):
+    """torch's default nn.Linear initialisation as a distribution (kaiming_uniform(a=sqrt 5) ->
+    U(-1/sqrt(in), 1/sqrt(in)) for weight and bias; weight_norm starts at g = ||v||, i.e. W = v), drawn
+    from our own generator with exact IEEE ops only so that the decoder is bit-reproducible from the seed."""
+    out_f, in_f = (mod.weight_v.shape if hasattr(mod, "weight_v") else mod.weight.shape)
+    bound = 1.0 / math.sqrt(in_f)
+    v = ((2.0 * _uniform(g, out_f, in_f) - 1.0) * bound).float()
+    b = ((2.0 * _uniform(g, out_f) - 1.0) * bound).float()
+    with torch.no_grad():
+        if hasattr(mod, "weight_v"):
+            mod.weight_v.copy_(v)
+            mod.weight_g.copy_(torch.sqrt(_sumsq(v.double())).float())
+        else:
+            mod.weight.copy_(v)
+        mod.bias.copy_(b)
+
+
 def make_decoder(seed: int, kind="separate", latent_size=256, point_feat_size=9,
-                 encode_style="both", network_specs=None, use_classifier=False):
-    """Reproducible decoder; hidden layers roughly variance preserving."""
+                 encode_style="both", network_specs=None, use_classifier=False,
+                 init="engineered", out_gain=1.0, bias_shift=None):
+    """Reproducible decoder; hidden layers roughly variance preserving.
+
+    ``init``: "engineered" -- random hidden units + a block wired to an ellipsoid level set (_engineer:
+                              numerically benign, a closed surface inside the cube);
+              "plain"      -- the same random generator WITHOUT the wiring, last layer scaled by
+                              ``out_gain`` (|sdf| up to ~0.1 / 0.4 / 0.95 for gain 1 / 4 / 16);
+              "default"    -- torch's default initialisation, |sdf| ~ 0.02.
+    The non-engineered variants get their last-layer biases shifted so that ~30 % of a coarse grid is
+    negative for the sample of the same seed (random nets have no zero crossing, SURVEY.md App. D);
+    ``bias_shift`` replays recorded shifts (fixtures) instead of recomputing them (quantile + tanh are
+    not bit-reproducible across hosts); the shifts used are left in ``dec.bias_shift``."""
     ns = dict(NETWORK_SPECS if network_specs is None else network_specs)
     cls = SeparateDecoder if kind == "separate" else CombinedDecoder
     with torch.random.fork_rng(devices=[]):
@@ -123,24 +151,44 @@ def make_decoder(seed: int, kind="separate", latent_size=256, point_feat_size=9,
         dec = cls(latent_size, point_feat_size, encode_style, use_classifier=use_classifier, **ns)
     g = _gen(7_000_001 * (seed + 1))
     has_ln = False
+    if init not in ("engineered", "plain", "default"):
+        raise ValueError(f"unknown init {init!r}")
     for name, mod in dec.named_children():  # registration order == deterministic
         if hasattr(mod, "weight_v") or isinstance(mod, torch.nn.Linear):
-            _fill_linear(g, mod, 1.0)
+            if init == "default":
+                _fill_default(g, mod)
+            else:
+                _fill_linear(g, mod, 1.0)
         elif isinstance(mod, torch.nn.LayerNorm):
             has_ln = True
             with torch.no_grad():
                 mod.weight.copy_((1.0 + 0.2 * _gauss(g, *mod.weight.shape)).float())
                 mod.bias.copy_((0.1 * _gauss(g, *mod.bias.shape)).float())
-    if has_ln:
-        return _center_outputs(dec, seed, latent_size, point_feat_size, encode_style).eval()
+    if init != "engineered":
+        sep = isinstance(dec, SeparateDecoder)
+        n_lin = (dec.num_hand_layers if sep else dec.num_layers) - 1
+        with torch.no_grad():
+            for prefix in (("linh", "lino") if sep else ("lin",)):
+                getattr(dec, f"{prefix}{n_lin - 1}").weight.mul_(float(out_gain))
+    if has_ln or init != "engineered":
+        return _center_outputs(dec, seed, latent_size, point_feat_size, encode_style,
+                               shifts=bias_shift).eval()
     return _engineer(dec, seed).eval()
 
 
-def _center_outputs(dec, seed, latent_size, point_feat_size, encode_style, frac_negative=0.3):
+def _center_outputs(dec, seed, latent_size, point_feat_size, encode_style, frac_negative=0.3, shifts=None):
     """LayerNorm decoders: the ellipsoid wiring of _engineer does not survive the normalisation, so the
     last-layer biases are shifted until ``frac_negative`` of a coarse grid (for the sample of the same
     seed) is inside -- a zero level set exists and the bbox re-grid is exercised."""
     from . import packer
+    sep = isinstance(dec, SeparateDecoder)
+    n_lin = (dec.num_hand_layers if sep else dec.num_layers) - 1
+    if shifts is not None:                 # replay recorded shifts (fixtures)
+        with torch.no_grad():
+            for o, prefix in enumerate(("linh", "lino") if sep else ("lin", "lin")):
+                getattr(dec, f"{prefix}{n_lin - 1}").bias[o if not sep else 0] -= float(shifts[o])
+        dec.bias_shift = [float(x) for x in shifts]
+        return dec
     sample = make_sample(seed, latent_size, point_feat_size, encode_style)
     ax = torch.linspace(-1, 1, 9)
     xyz = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
@@ -149,13 +197,14 @@ def _center_outputs(dec, seed, latent_size, point_feat_size, encode_style, frac_
     dec.eval()
     with torch.no_grad():
         out = dec(x)
-        sep = isinstance(dec, SeparateDecoder)
-        n_lin = (dec.num_hand_layers if sep else dec.num_layers) - 1
+        used = []
         for o, prefix in enumerate(("linh", "lino") if sep else ("lin", "lin")):
             pre = torch.atanh(out[o][:, 0].double().clamp(-0.999999, 0.999999))
-            shift = torch.quantile(pre, frac_negative)
+            shift = torch.quantile(pre, frac_negative).float()
             last = getattr(dec, f"{prefix}{n_lin - 1}")
-            last.bias[o if not sep else 0] -= shift.float()
+            last.bias[o if not sep else 0] -= shift
+            used.append(float(shift))
+    dec.bias_shift = used
     return dec
 
 

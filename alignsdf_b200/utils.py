@@ -36,16 +36,19 @@ def get_nerf_embedder(multires):
 
 def decode_sdf_multi_output(decoder, latent_vector, queries, mano_results, cam_intr, specs):
     """queries are already-embedded features [P, PointFeatSize] (what the reference passes);
-    returns (sdf_hand [P,1], sdf_obj [P,1], predicted_class)."""
+    returns (sdf_hand [P,1], sdf_obj [P,1], predicted_class) where predicted_class is what the reference's
+    decoder returns as its third output: the raw classifier logits [P, num_class] (networks/model.py:161-162,188)
+    or ``Tensor([0])`` when the decoder has no classifier head (:188,350)."""
     if specs.get('PixelAlign', False):
-        raise NotImplementedError("PixelAlign is a 'next' row (SURVEY.md §8f.2)")
+        from . import pixel_align
+        return pixel_align.decode_sdf_multi_output(decoder, latent_vector, queries, mano_results, cam_intr, specs)
     eng = _engine.get_engine(decoder, queries.device)
     bound = eng.bind(latent_vector, specs, mano_results, None, feature_mode=True)
     want_cls = eng.topo.classifier is not None
-    hand, obj, cls = bound.eval_points(queries, want_cls=want_cls)
+    hand, obj, cls = bound.eval_points(queries, want_cls=want_cls, want_logits=want_cls)
     if obj is None:
         obj = torch.zeros_like(hand)
-    predicted = cls if want_cls else torch.zeros(1, device=queries.device)
+    predicted = cls[1] if want_cls else torch.zeros(1, device=queries.device)
     return hand.unsqueeze(1), obj.unsqueeze(1), predicted
 
 

@@ -329,7 +329,7 @@ def main():
                                     traffic_note="dram__bytes_read+write of one 256^3 launch, ncu --set full "
                                                  "(profiles/r01_ncu_tc3_eval_256.txt); algorithmic HBM bytes = 8 B/query",
                                     ms_per_launch=k1, queries_per_launch=N ** 3, flop_per_query=F_MIN,
-                                    issued_tflops_f16_equiv=issued, fallbacks_to_fp16_kernel=engine.FALLBACKS["tc3_to_tc2"],
+                                    issued_tflops_f16_equiv=issued, fallbacks_to_fp16_kernel=engine.STATS["f8_rejected"],
                                     frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
                                     Mq_per_s_kernel=N ** 3 / (k1 * 1e-3) / 1e6)
         if world == 1 and not args.no_cpu_baseline:

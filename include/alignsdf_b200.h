@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ASDF_ABI_VERSION 1
+#define ASDF_ABI_VERSION 2
 #define ASDF_MAX_LAYERS 8
 #define ASDF_MAX_POINT_DIM 64
 
@@ -72,62 +72,83 @@ typedef struct {
  * networks/model.py:254-255,317-319);   static_dev: WxT blocks, sample_dev: [npad][D+1] blocks,
  * cls_dev: [n_class][h_last+1] (weights then bias) or NULL.
  * out_hand_dev / out_obj_dev: [end-begin] f32.  out_cls_dev: [end-begin] int32 argmax or NULL.
+ * out_logits_dev: [end-begin][n_class] f32 raw classifier logits (what the reference's decoder returns as its
+ * third output, networks/model.py:161-162,188) or NULL.
  * bbox_dev: int32[12] = hand {min0,min1,min2,max0,max1,max2} then object {...}, updated with
  * atomicMin/Max over the unravelled indices of every point whose field is < 0
  * (utils/mesh.py:198-247); the caller initialises it to {INT_MAX x3, -1 x3} x2.  May be NULL. */
 int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev, const float* sample_dev,
                    const float* cls_dev, const asdf_query* q, float* out_hand_dev, float* out_obj_dev,
-                   int32_t* out_cls_dev, int32_t* bbox_dev, void* stream);
+                   int32_t* out_cls_dev, float* out_logits_dev, int32_t* bbox_dev, void* stream);
 
-/* Tensor-core path for the shipped topology (two 5-layer 512-wide MLPs, skip at layer 2,
- * utils/mesh.py:46-63,96-115 hot loops): tcgen05 / TMEM, fp16 x3 split precision. */
+/* Tensor-core path (csrc/k1_tc.cu) for the shipped topology -- 5 linear layers, 512 wide, skip into layer 2:
+ * SeparateDecoder (two MLPs, networks/model.py:285-350) or CombinedDecoder without xyz_in_all (one MLP, two outputs,
+ * networks/model.py:139-188) -- replacing the hot loops of utils/mesh.py:46-63,96-115 for a BATCH of samples per
+ * launch: tcgen05 / TMEM, fp32 accumulation, split precision.
+ *   ASDF_TC_F16X3   x.W ~= hi16(x).hi16(W) + lo16(x).hi16(W) + hi16(x).lo16(W): within the 1e-5 contract for any decoder
+ *   ASDF_TC_F16_F8  the two correction products in e4m3 (2/3 of the tensor time): only for decoders whose
+ *                   calibration run shows them inside the contract (alignsdf_b200/engine.py)
+ * static_dev: asdf_tc_static_bytes(n_decoders) bytes (alignsdf_b200/tc_pack.py, one stream per kind);
+ * samples_dev: per sample asdf_tc_sample_bytes() bytes written by asdf_tc_bind (sample_stride apart);
+ * grid_dev: NULL or float[n_samples][4] = {voxel, origin0, origin1, origin2} overriding q->voxel / q->origin per
+ *   sample (e.g. written by asdf_regrid: pass 2 then needs no host round trip);
+ * out_*_dev: NULL (bounding-box-only pass: utils/mesh.py:46-80 only uses pass 1 for the box) or [n_samples][out_stride];
+ * bbox_dev: NULL or int32[n_samples][12] (initialised by the caller like asdf_simt_eval's);
+ * status_dev: int32[1], zeroed by the caller; bit 0 is raised when an activation left the range of the operand
+ *   format (e4m3: 448, fp16: 60000 / 16) -- the outputs of that launch must then be discarded and the query re-run
+ *   through the next safer kernel (F16_F8 -> F16X3 -> asdf_simt_eval). */
+#define ASDF_TC_F16X3 0
+#define ASDF_TC_F16_F8 1
 typedef struct {
-  int32_t h[2];            /* width of layer 1 per branch (512 - d0), <= 256 */
-  float act_scale;         /* power of two applied to activations before the fp16 split */
-  float w_scale[2][3];     /* power of two applied to the weights of layers 1..3, per branch */
-  int64_t branch_stride;   /* bytes between the two branches' packed weight streams */
-  void* debug_dev;         /* NULL, or int64[16] receiving phase cycle counters of CTA pair 0 */
-} asdf_tc_desc;
-int asdf_tc_eval(const asdf_tc_desc* desc, const void* static_dev, const float* sample_dev,
-                 const asdf_query* q, float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev,
-                 void* stream);
-/* Second-generation tensor-core path (csrc/k1_tc2.cu): 128 points per CTA, activation hi-halves in
- * tensor memory, biases / point terms folded into K=16 UMMAs.  Same outputs as asdf_tc_eval.
- * static_dev: asdf_tc2_static_bytes() bytes, sample_dev: asdf_tc2_sample_bytes() bytes
- * (layouts in alignsdf_b200/tc2_pack.py). */
-int asdf_tc2_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
-                  float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream);
-/* Same, additionally filling debug_dev (int64[32]) with cycle counters of CTA pair 0. */
-int asdf_tc2_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
-                        float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, void* stream,
-                        void* debug_dev);
-int64_t asdf_tc2_static_bytes(void);
-int64_t asdf_tc2_sample_bytes(void);
+  int32_t kind;
+  int32_t n_decoders;
+  int32_t n_samples;
+  int32_t reserved;
+  const void* static_dev;
+  const void* samples_dev;
+  int64_t sample_stride;
+  const float* grid_dev;
+  float* out_hand_dev;
+  float* out_obj_dev;
+  int64_t out_stride;
+  int32_t* bbox_dev;
+  int32_t* status_dev;
+} asdf_tc_launch;
+int asdf_tc_eval(const asdf_tc_launch* l, const asdf_query* q, void* stream);
+int64_t asdf_tc_static_bytes(int32_t n_decoders);
+int64_t asdf_tc_sample_bytes(void);
 
-/* Third-generation tensor-core path (csrc/k1_tc3.cu): the asdf_tc2_eval data flow with the two
- * split-precision correction products in fp8 (kind::f8f6f4, e4m3) -- 8 instead of 12 UMMAs per
- * 64-wide K chunk.  Same outputs and contract (|sdf - reference| <= 1e-5).
- * static_dev: asdf_tc3_static_bytes() bytes, sample_dev: asdf_tc3_sample_bytes() bytes (layouts in
- * alignsdf_b200/tc3_pack.py).  status_dev: int32[1], zeroed by the caller; bit 0 is raised when an
- * activation exceeded the range of the fp8 operands -- the outputs of that launch must then be
- * discarded and the query re-run through asdf_tc2_eval (alignsdf_b200/engine.py does). */
-int asdf_tc3_eval(const void* static_dev, const void* sample_dev, const asdf_query* q,
-                  float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
-                  void* stream);
-/* Same, additionally filling debug_dev (int64[512], zeroed by the caller) with cycle counters of CTA pair 0. */
-int asdf_tc3_eval_debug(const void* static_dev, const void* sample_dev, const asdf_query* q,
-                        float* out_hand_dev, float* out_obj_dev, int32_t* bbox_dev, int32_t* status_dev,
-                        void* stream, void* debug_dev);
-int64_t asdf_tc3_static_bytes(void);
-int64_t asdf_tc3_sample_bytes(void);
+/* Per-sample set-up of the tensor-core path on the device (csrc/bind.cu).  Replaces what the reference recomputes
+ * for every query point: the latent columns of the first / skip layer (utils/utils.py:561-572 cat + networks/model.py:
+ * 304-311 lin0 / lin2) fold into biases, the pose-align features (utils/utils.py:376-430) into [512,3] point matrices
+ * (float64), which are then scaled, split into fp16 hi + lo and written as the "P tiles" asdf_tc_eval streams.
+ * static_dev: per decoder (decoder_stride doubles apart)  Wz[2][512][latent_size] | Wf[2][512][ASDF_MAX_POINT_DIM] |
+ *   b[4][512]  (latent / feature columns of layers 0 and 2; biases of layers 0..3, b1 zero padded);
+ * latent_dev: float[n_samples][latent_size];  affine_dev: double[n_samples][ASDF_MAX_POINT_DIM][4] = rows (A, c) of
+ *   features = A.xyz + c;  feature_index[d][f]: which affine row feeds feature f of decoder d (networks/model.py:288-299);
+ * fold_scratch_dev: double[n_samples][n_decoders][2][512][4];  samples_dev: n_samples blocks of
+ *   asdf_tc_sample_bytes() bytes, zero-initialised once by the caller;
+ * status_dev: bit 1 is raised when the operands of a sample do not fit fp16 (caller falls back to asdf_simt_eval). */
+typedef struct {
+  int32_t n_decoders;
+  int32_t latent_size;
+  int32_t n_features[2];
+  int32_t feature_index[2][ASDF_MAX_POINT_DIM];
+  int64_t decoder_stride;
+  float act_scale;       /* t: 16 for ASDF_TC_F16X3, 1 for ASDF_TC_F16_F8 */
+  float p_absmax;        /* bound on |xyz| of the queries the block will be used for */
+  double w_scale[2][3];  /* power-of-two scales of the packed weights of layers 1..3 (tc_pack.py) */
+} asdf_tc_bind_desc;
+int asdf_tc_bind(const asdf_tc_bind_desc* desc, const double* static_dev, const float* latent_dev,
+                 const double* affine_dev, int32_t n_samples, double* fold_scratch_dev, void* samples_dev,
+                 int64_t sample_stride, int32_t* status_dev, void* stream);
+int64_t asdf_tc_bind_static_doubles(int32_t n_decoders, int32_t latent_size);
 
-/* Layout self test of the tensor-core path: D[128,256] = A[128,64] . B[256,64]^T through the same
- * operand layouts / descriptors / TMEM read-back as asdf_tc_eval (a_rows_dev fp16 row-major,
- * b_tiles_dev two pre-swizzled 16 KiB tiles, d_out_dev f32). */
-int asdf_tc_selftest(const void* a_rows_dev, const void* b_tiles_dev, float* d_out_dev, void* stream);
-/* Bytes of the packed static stream / floats of the per-sample block the tcgen05 path expects. */
-int64_t asdf_tc_static_bytes(void);
-int64_t asdf_tc_sample_floats(void);
+/* Bounding boxes of pass 1 -> lattice of pass 2 (utils/mesh.py:198-256 get_higher_res_cube, same f32 arithmetic):
+ * bbox_dev int32[n_samples][12], branch_mask bit0 hand / bit1 object, voxel = spacing of pass 1 (origin -1);
+ * grid_dev float[n_samples][4] = {new_voxel, new_origin[3]}, minmax_dev NULL or float[n_samples][6]. */
+int asdf_regrid(const int32_t* bbox_dev, int32_t n_samples, int32_t branch_mask, int32_t N, float voxel,
+                float* grid_dev, float* minmax_dev, void* stream);
 
 /* Query coordinates only (tests / debugging): xyz_dev [end-begin,3], bit-exact w.r.t. the
  * reference's torch expressions at utils/mesh.py:32-40,86-94. */

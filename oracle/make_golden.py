@@ -66,6 +66,15 @@ CASES = [
     # LayerNorm instead of weight norm (NetworkSpecs.weight_norm = false, networks/model.py:254-255,317-319)
     dict(name="sep_ln_both9_n12", kind="separate", pf=9, style="both", N=12, seed=13, weight_norm=False),
     dict(name="comb_ln_both9_n12", kind="combined", pf=9, style="both", N=12, seed=14, weight_norm=False),
+    # NON-engineered decoders: the plain random generator without the ellipsoid wiring, last layer
+    # x1 / x4 / x16 (|sdf| up to ~0.1 / 0.45 / 0.97), and torch's default initialisation; last-layer
+    # biases shifted so ~30 % of the cube is inside (the shifts are recorded in the fixture's meta)
+    dict(name="sep_plain_g1_n32", kind="separate", pf=9, style="both", N=32, seed=20, init="plain", out_gain=1.0),
+    dict(name="sep_plain_g4_n32", kind="separate", pf=9, style="both", N=32, seed=21, init="plain", out_gain=4.0),
+    dict(name="sep_plain_g16_n32", kind="separate", pf=9, style="both", N=32, seed=22, init="plain", out_gain=16.0),
+    dict(name="sep_default_n32", kind="separate", pf=9, style="both", N=32, seed=23, init="default"),
+    dict(name="comb_plain_g4_n24", kind="combined", pf=9, style="both", N=24, seed=24, init="plain", out_gain=4.0),
+    dict(name="comb_default_n16", kind="combined", pf=9, style="both", N=16, seed=25, init="default"),
 ]
 
 
@@ -105,7 +114,8 @@ def run_reference_case(case):
     if case.get("weight_norm") is False:
         ns["weight_norm"] = False
     use_cls = bool(case.get("use_classifier", False))
-    mine = synthetic.make_decoder(seed, kind, 256, pf, style, ns, use_classifier=use_cls)
+    mine = synthetic.make_decoder(seed, kind, 256, pf, style, ns, use_classifier=use_cls,
+                                  init=case.get("init", "engineered"), out_gain=case.get("out_gain", 1.0))
     sample = synthetic.make_sample(seed, 256, pf, style)
 
     ref_cls = ref_model.SeparateDecoder if kind == "separate" else ref_model.CombinedDecoder
@@ -198,7 +208,10 @@ def run_reference_case(case):
         errs["p1o"] = float(np.abs(res["pass1_obj"].numpy() - p1o).max())
         errs["p2o"] = float(np.abs(res["obj"].numpy() - vols["obj"]).max())
     # LayerNorm decoders amplify fp32 summation-order noise (outputs span the whole tanh range): 2e-6 there
-    assert max(errs.values()) <= (2e-6 if case.get("weight_norm") is False else 1e-6), errs
+    # non-engineered decoders with a large last-layer gain: the fp32 summation-order noise of two faithful fp32
+    # evaluations grows with the output range (measured 1.0e-6 .. 1.9e-6 at gain 4, 4.5e-6 at gain 16)
+    tol = 2e-6 if case.get("weight_norm") is False else 1e-6 * max(1.0, case.get("out_gain", 1.0) / 2.0)
+    assert max(errs.values()) <= tol, errs
     cls = None
     if cap.logits:
         lg = np.concatenate(cap.logits, 0)
@@ -206,6 +219,8 @@ def run_reference_case(case):
         assert np.array_equal(res["cls"].numpy().reshape(-1).astype(np.int32), cls)
 
     meta = dict(case)
+    if getattr(mine, "bias_shift", None) is not None:
+        meta["bias_shift"] = [float(x) for x in mine.bias_shift]
     meta.update(latent_size=256, network_specs=ns, digest=synthetic.state_digest(mine),
                 oracle_vs_reference_maxerr=errs, torch=torch.__version__,
                 frac_neg_hand=float((p1h < 0).mean()) if p1h is not None else None,
@@ -297,6 +312,19 @@ def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     index = {}
+    only = set(sys.argv[1:])
+    if only:                                   # regenerate just the named cases, keep the rest of the index
+        with open(os.path.join(gold, "index.json")) as f:
+            index = json.load(f)
+        for case in CASES:
+            if case["name"] in only:
+                out, meta = run_reference_case(case)
+                np.savez_compressed(os.path.join(gold, case["name"] + ".npz"), **out)
+                index[case["name"]] = meta
+                print(case["name"], meta["oracle_vs_reference_maxerr"], "neg frac", meta["frac_neg_hand"], meta["frac_neg_obj"])
+        with open(os.path.join(gold, "index.json"), "w") as f:
+            json.dump(index, f, indent=1, sort_keys=True)
+        return
     for case in CASES:
         out, meta = run_reference_case(case)
         np.savez_compressed(os.path.join(gold, case["name"] + ".npz"), **out)

@@ -24,7 +24,9 @@ def load_case(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     dec = synthetic.make_decoder(meta["seed"], meta["kind"], meta["latent_size"], meta["pf"],
                                  meta["style"], meta["network_specs"],
-                                 use_classifier=meta.get("use_classifier", False))
+                                 use_classifier=meta.get("use_classifier", False),
+                                 init=meta.get("init", "engineered"), out_gain=meta.get("out_gain", 1.0),
+                                 bias_shift=meta.get("bias_shift"))
     sample = synthetic.make_sample(meta["seed"], meta["latent_size"], meta["pf"], meta["style"])
     return meta, g, dec, sample
 

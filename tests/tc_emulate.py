@@ -1,76 +1,106 @@
-"""Numpy emulation of csrc/k1_tc.cu's arithmetic, driven by the *packed* buffers (test helper).
-
-It un-swizzles the streamed tiles exactly as the kernel's UMMAs consume them (tile order, A-slot
-mapping, scales) and models each UMMA triple as a_hi.b_hi + a_lo.b_hi + a_hi.b_lo with exact fp16
-products accumulated in (at least) fp32.  Used on the CPU to validate the packing order and the
-fp16x3 precision against the reference's golden fields before any GPU time is spent."""
+"""Numpy emulation of csrc/k1_tc.cu's arithmetic from the *packed* buffers (test helper): point operand,
+P tiles (bias + point term as a K=16 fp16 product), main tiles in stream order, position remapping of
+layer 3, scales -- for both precision kinds:
+    F16X3   hi16(x).hi16(W) + lo16(x).hi16(W) + hi16(x).lo16(W)
+    F16_F8  hi16(x).hi16(W) + e4m3(2^10 lo(x)).e4m3(2^-10 W) + e4m3(hi16(x)).e4m3(lo(W))
+and both decoder families (two MLPs with one output each / one MLP with two outputs)."""
 import numpy as np
 
 from alignsdf_b200 import tc_pack as T
 
 
-def _split(v32):
-    v = np.minimum(v32, np.float32(60000.0)).astype(np.float32)
+def _split(v32, kind):
+    """epilogue of layers 0..2 (as float64 values): F16X3 -> (hi16, lo16, None); F16_F8 -> (hi16, lo8, x8)"""
+    if kind == T.F16X3:
+        v = np.minimum(np.maximum(v32, 0), np.float32(60000.0)).astype(np.float32)
+        hi = v.astype(np.float16)
+        lo = (v - hi.astype(np.float32)).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64), None
+    v = np.maximum(v32, 0).astype(np.float32)
     hi = v.astype(np.float16)
-    lo = (v - hi.astype(np.float32)).astype(np.float16)
-    return hi.astype(np.float64), lo.astype(np.float64)
+    lo = (v - hi.astype(np.float32)).astype(np.float32)
+    lo8 = T.e4m3_decode(T.e4m3_encode(lo * np.float32(T.LO_SCALE)))
+    x8 = T.e4m3_decode(T.e4m3_encode(hi.astype(np.float32)))
+    return hi.astype(np.float64), lo8.astype(np.float64), x8.astype(np.float64)
 
 
-def _tiles(raw, d):
-    s = raw[:2 * 2 * T.TILES_PER_DECODER * T.TILE_BYTES].view(np.float16).reshape(2, 2, T.TILES_PER_DECODER, -1)
-    return [[T.unswizzle_tile(s[d, c, i]).astype(np.float64) for i in range(T.TILES_PER_DECODER)] for c in range(2)]
-
-
-def _layer(tiles, first, n_blocks, kchunks, slot_of, a_hi, a_lo):
-    """accumulators [P, 256*n_blocks]; a_* are dicts slot -> [P,64]."""
-    P = next(iter(a_hi.values())).shape[0]
-    out = np.zeros((P, 256 * n_blocks))
-    i = first
-    for nb in range(n_blocks):
-        for kc in range(kchunks):
-            s = slot_of(kc)
-            for c in range(2):
-                bhi, blo = tiles[c][i], tiles[c][i + 1]
-                cols = slice(256 * nb + 128 * c, 256 * nb + 128 * c + 128)
-                out[:, cols] += a_hi[s] @ bhi.T + a_lo[s] @ bhi.T + a_hi[s] @ blo.T
-            i += 2
-    return out.astype(np.float32), i
-
-
-def emulate(raw_static, sample, xyz):
-    """-> (sdf_hand [P], sdf_obj [P]) float32."""
+def emulate(raw_static, raw_sample, xyz, kind=T.F16X3, n_dec=2, want_max=False):
     raw_static = np.asarray(raw_static, np.uint8)
-    params = raw_static[2 * 2 * T.TILES_PER_DECODER * T.TILE_BYTES:].view(np.float32).reshape(2, T.STATIC_PARAM_FLOATS)
-    samp = np.asarray(sample, np.float32).reshape(2, 2, 512, 4)
+    raw_sample = np.asarray(raw_sample, np.uint8)
+    nmain = n_dec * 2 * T.MAIN_TILES * T.TILE_BYTES
+    main = raw_static[:nmain].reshape(n_dec, 2, T.MAIN_TILES, T.TILE_BYTES)
+    params = raw_static[nmain:].view(np.float32).reshape(2, T.STATIC_PARAM_FLOATS)
+    ptiles = raw_sample[:T.SAMPLE_TILE_BYTES].view(np.float16).reshape(2, 2, T.P_TILES, T.TILE_ELEMS)
+    scal = raw_sample[T.SAMPLE_TILE_BYTES:].view(np.float32)
+    cp, c1 = np.float32(scal[2]), np.float32(scal[3])
     p = np.asarray(xyz, np.float32)
+    P = p.shape[0]
+    # point operand (fp16): k0..7 = [p_h(3), c1, p_l(3), 0], k8..15 = [p_h(3), c1, 0...]
+    s = (p * cp).astype(np.float32)
+    ph = s.astype(np.float16)
+    pl = (s - ph.astype(np.float32)).astype(np.float16)
+    ap = np.zeros((P, 16), np.float64)
+    ap[:, 0:3], ap[:, 3] = ph, np.float16(c1)
+    ap[:, 4:7] = pl
+    ap[:, 8:11], ap[:, 11] = ph, np.float16(c1)
     outs = []
-    for d in range(2):
-        tiles = _tiles(raw_static, d)
-        b1s, b3w4 = params[d, :256], params[d, 256:1280].reshape(512, 2)
-        b4, inv1, inv2, inv3 = params[d, 1280:1284]
-        m0, m2 = samp[d, 0], samp[d, 1]
+    vmax = 0.0
+    for d in range(n_dec):
+        inv1, inv2, inv3 = params[d, 513:516]
+        inv0 = scal[d]
+        mi = [0]
+        pi = [0]
 
-        def affine(m):
-            # fmaf(m.x, px, fmaf(m.y, py, fmaf(m.z, pz, m.w))) -- evaluated in float64 then rounded
-            return (p.astype(np.float64) @ m[:, :3].astype(np.float64).T + m[:, 3].astype(np.float64)).astype(np.float32)
-        x1 = np.maximum(affine(m0), 0)
-        hi, lo = _split(x1)
-        a_hi = {s: hi[:, 64 * s:64 * s + 64] for s in range(8)}
-        a_lo = {s: lo[:, 64 * s:64 * s + 64] for s in range(8)}
-        acc1, i = _layer(tiles, 0, 1, 8, lambda kc: kc, a_hi, a_lo)
-        x2 = np.maximum(acc1 * inv1 + b1s[None], 0).astype(np.float32)
-        hi, lo = _split(x2)
-        for s in range(4):
-            a_hi[s], a_lo[s] = hi[:, 64 * s:64 * s + 64], lo[:, 64 * s:64 * s + 64]
-        acc2, i = _layer(tiles, i, 2, 4, lambda kc: kc, a_hi, a_lo)
-        x3 = np.maximum(acc2 * inv2 + affine(m2), 0).astype(np.float32)
-        hi, lo = _split(x3)
-        for f in range(8):                       # feature chunk f -> slot (f+4)%8
-            s = (f + 4) % 8
-            a_hi[s], a_lo[s] = hi[:, 64 * f:64 * f + 64], lo[:, 64 * f:64 * f + 64]
-        acc3, i = _layer(tiles, i, 2, 8, lambda j: (j + 4) % 8, a_hi, a_lo)
-        assert i == T.TILES_PER_DECODER
-        x4 = np.maximum(acc3 * inv3 + b3w4[None, :, 0], 0).astype(np.float32)
-        s4 = (x4.astype(np.float64) @ b3w4[:, 1].astype(np.float64)).astype(np.float32)
-        outs.append(np.tanh(s4 + b4).astype(np.float32))
+        def ptile_acc():
+            acc = np.zeros((P, 128))
+            for c in range(2):
+                tile = T.unswizzle_tile(ptiles[d, c, pi[0]]).astype(np.float64)      # [64, 64]
+                acc[:, 64 * c:64 * c + 64] = ap @ tile[:, :16].T
+            pi[0] += 1
+            return acc
+
+        def main_acc(acc, a_hi, a_c1, a_c2, positions):
+            for pos in positions:
+                for c in range(2):
+                    bhi = T.unswizzle_tile(main[d, c, mi[0]].view(np.float16)).astype(np.float64)
+                    cols = slice(64 * c, 64 * c + 64)
+                    if kind == T.F16X3:
+                        blo = T.unswizzle_tile(main[d, c, mi[0] + 1].view(np.float16)).astype(np.float64)
+                        acc[:, cols] += a_hi[pos] @ bhi.T + a_c1[pos] @ bhi.T + a_hi[pos] @ blo.T
+                    else:
+                        b8 = T.e4m3_decode(T.unswizzle_tile8(main[d, c, mi[0] + 1])).astype(np.float64)   # [64, 128]
+                        acc[:, cols] += a_hi[pos] @ bhi.T + a_c1[pos] @ b8[:, :64].T + a_c2[pos] @ b8[:, 64:].T
+                mi[0] += 2
+            return acc
+
+        a_hi, a_c1, a_c2 = {}, {}, {}
+
+        def store(layer_out, inv, pos_of):
+            nonlocal vmax
+            x = (layer_out.astype(np.float32) * np.float32(inv)).astype(np.float32)
+            vmax = max(vmax, float(x.max()))
+            hi, k1, k2 = _split(x, kind)
+            for cidx in range(x.shape[1] // 64):
+                sl = slice(64 * cidx, 64 * cidx + 64)
+                a_hi[pos_of(cidx)], a_c1[pos_of(cidx)] = hi[:, sl], k1[:, sl]
+                a_c2[pos_of(cidx)] = None if k2 is None else k2[:, sl]
+
+        l0 = np.concatenate([ptile_acc() for _ in range(4)], 1).astype(np.float32)
+        store(l0, inv0, lambda c: c)
+        l1 = np.concatenate([main_acc(ptile_acc(), a_hi, a_c1, a_c2, range(8)) for _ in range(2)], 1).astype(np.float32)
+        store(l1, inv1, lambda c: c)
+        l2 = np.concatenate([main_acc(ptile_acc(), a_hi, a_c1, a_c2, range(4)) for _ in range(4)], 1).astype(np.float32)
+        store(l2, inv2, lambda c: (c + 4) % 8)
+        # layer 3 reads positions 4..7 first, except its last N block (natural order, chunks permuted in the stream)
+        l3 = np.concatenate([main_acc(ptile_acc(), a_hi, a_c1, a_c2,
+                                      [(j + 4) % 8 for j in range(8)] if nb < 3 else list(range(8)))
+                             for nb in range(4)], 1)
+        assert mi[0] == T.MAIN_TILES and pi[0] == T.P_TILES
+        x4 = np.maximum(l3.astype(np.float32) * np.float32(inv3), 0).astype(np.float32)
+        for o in ((d,) if n_dec == 2 else (0, 1)):       # one output per decoder, or both outputs of the one MLP
+            w4, b4 = params[o, :512], params[o, 512]
+            s4 = (x4.astype(np.float64) @ w4.astype(np.float64)).astype(np.float32)
+            outs.append(np.tanh(s4 + b4).astype(np.float32))
+    if want_max:
+        return outs, vmax
     return outs

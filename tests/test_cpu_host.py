@@ -26,7 +26,9 @@ def test_oracle_matches_reference_golden(name):
     """oracle/alignsdf_oracle.py vs outputs captured from the real reference (tol 1e-6; 2e-6 for the
     LayerNorm decoders, whose outputs span the whole tanh range and amplify fp32 summation-order noise)."""
     meta, g, dec, sample = helpers.load_case(name)
-    tol = 2e-6 if meta.get("weight_norm") is False else 1e-6
+    # non-engineered decoders with a large last-layer gain: two faithful fp32 evaluations differ by summation-order
+    # noise that grows with the output range (oracle/make_golden.py)
+    tol = 2e-6 if meta.get("weight_norm") is False else 1e-6 * max(1.0, meta.get("out_gain", 1.0) / 2.0)
     sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
     res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs,
                              sample.mano_results, sample.obj_results, meta["N"],
@@ -74,7 +76,7 @@ def test_folded_network_matches_reference_golden(name):
         u = xyz.numpy()
     out = packer.folded_forward_numpy(br, u, topo.pre_tanh)
     hand, obj = (out[0][:, 0], out[1][:, 0]) if topo.kind == "separate" else (out[0][:, 0], out[0][:, 1])
-    tol = 3e-6 if meta.get("weight_norm") is False else 1e-6
+    tol = 3e-6 if meta.get("weight_norm") is False else 1e-6 * max(1.0, meta.get("out_gain", 1.0) / 2.0)
     if "pass1_hand" in g:
         assert np.abs(hand - g["pass1_hand"].reshape(-1)).max() <= tol
     if "pass1_obj" in g:
@@ -154,7 +156,7 @@ def test_shared_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.asdf_abi_version.restype = ctypes.c_int
-    assert lib.asdf_abi_version() == 1
+    assert lib.asdf_abi_version() == 2
 
 
 def test_ctypes_structs_match_header_sizes(tmp_path):
@@ -164,15 +166,19 @@ def test_ctypes_structs_match_header_sizes(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "alignsdf_b200.h"\n'
-        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(asdf_query), sizeof(asdf_simt_desc),'
-        ' sizeof(asdf_tc_desc), sizeof(asdf_mc_params), offsetof(asdf_query, points_dev),'
-        ' offsetof(asdf_simt_desc, table), offsetof(asdf_mc_params, spacing), offsetof(asdf_tc_desc, branch_stride));return 0;}\n')
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(asdf_query), sizeof(asdf_simt_desc),'
+        ' sizeof(asdf_tc_launch), sizeof(asdf_mc_params), offsetof(asdf_query, points_dev),'
+        ' offsetof(asdf_simt_desc, table), offsetof(asdf_mc_params, spacing), offsetof(asdf_tc_launch, status_dev),'
+        ' sizeof(asdf_tc_bind_desc), offsetof(asdf_tc_bind_desc, decoder_stride), offsetof(asdf_tc_bind_desc, w_scale),'
+        ' offsetof(asdf_tc_launch, grid_dev));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [ctypes.sizeof(_lib.Query), ctypes.sizeof(_lib.SimtDesc), ctypes.sizeof(_lib.TcDesc),
+    want = [ctypes.sizeof(_lib.Query), ctypes.sizeof(_lib.SimtDesc), ctypes.sizeof(_lib.TcLaunch),
             ctypes.sizeof(_lib.McParams), _lib.Query.points_dev.offset, _lib.SimtDesc.table.offset,
-            _lib.McParams.spacing.offset, _lib.TcDesc.branch_stride.offset]
+            _lib.McParams.spacing.offset, _lib.TcLaunch.status_dev.offset,
+            ctypes.sizeof(_lib.TcBindDesc), _lib.TcBindDesc.decoder_stride.offset, _lib.TcBindDesc.w_scale.offset,
+            _lib.TcLaunch.grid_dev.offset]
     assert got == want
 
 

@@ -119,12 +119,32 @@ def test_points_and_feature_queries_match_oracle(dev, path):
                                            s.specs["SdfScaleFactor"], s.obj_results, "both")
         ref_feats = orc.embed(xyz, sample.specs, sample.mano_results, sample.obj_results)
         assert (feats.cpu() - ref_feats).abs().max() <= 5e-6
-        fh, fo, _ = autils.decode_sdf_multi_output(dec, s.latent, feats, s.mano_results, None, s.specs)
+        fh, fo, third = autils.decode_sdf_multi_output(dec, s.latent, feats, s.mano_results, None, s.specs)
         assert fh.shape == (1000, 1)
+        assert third.shape == (1,) and float(third[0]) == 0.0                # networks/model.py:350 Tensor([0])
         assert (fh[:, 0].cpu() - h[:, 0]).abs().max() <= TOL and (fo[:, 0].cpu() - o[:, 0]).abs().max() <= TOL
     # empty query
     eh, eo, _ = autils.decode_sdf_points(dec, s.latent, xyz[:0].to(dev), s.mano_results, s.obj_results, s.specs)
     assert eh.numel() == 0 and eo.numel() == 0
+
+
+def test_decode_sdf_multi_output_returns_the_class_logits(dev):
+    """the third output of a decoder with a classifier head is the raw logits [P, num_class]
+    (networks/model.py:161-162,188) -- reference-style callers take .argmax(dim=1) of it (utils/mesh.py:60,112,157)."""
+    meta, g, dec, sample = helpers.load_case("comb_cls_n12")
+    s = helpers.to_cuda(sample)
+    xyz = torch.rand(700, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    feats = autils.kinematic_embedding(xyz.to(dev), s.mano_results, 700, 9, s.specs["SdfScaleFactor"], s.obj_results, "both")
+    h, o, logits = autils.decode_sdf_multi_output(dec, s.latent, feats, s.mano_results, None, s.specs)
+    assert h.shape == (700, 1) and o.shape == (700, 1) and logits.shape == (700, 6) and logits.dtype == torch.float32
+    with torch.no_grad():
+        rh, ro, rl = orc.decode_points(dec.state_dict(), orc.decoder_cfg(dec), sample.latent, xyz, sample.specs,
+                                       sample.mano_results, sample.obj_results)
+    assert (h.cpu() - rh).abs().max() <= TOL and (o.cpu() - ro).abs().max() <= TOL
+    assert (logits.cpu() - rl).abs().max() <= 1e-4 * max(1.0, float(rl.abs().max()))
+    top2 = rl.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert torch.equal(logits.argmax(dim=1).cpu()[clear], rl.argmax(dim=1)[clear])
 
 
 def test_torch_fp32_reference_forward_on_gpu(dev):
@@ -224,9 +244,22 @@ def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
         assert np.array_equal(rf, ef) and np.array_equal(rv, ev.astype(np.float32))
         assert np.array_equal(np.asarray(res[tag].faces), ef)
     if label:
+        # utils/mesh.py:137-184: the decoder re-queried at the marching-cubes vertices, argmax of the class logits
         lab = np.load(prefix + "_hand_label.npz")
         assert lab["points"].shape[0] == lab["labels"].shape[0] > 0
-        assert set(np.unique(lab["labels"])) <= set(range(6))
+        v, _, _ = mo.marching_cubes(vols["hand"].cpu().numpy(), 0.0, [vs] * 3)
+        want_pts = v.copy()
+        for k in range(3):
+            want_pts[:, k] = np.float32(org[k]) + want_pts[:, k]
+        assert np.array_equal(lab["points"], want_pts)                       # every vertex, origin-shifted
+        with torch.no_grad():
+            _, _, logits = orc.decode_points(dec.state_dict(), orc.decoder_cfg(dec), sample.latent,
+                                             torch.from_numpy(want_pts), sample.specs, sample.mano_results,
+                                             sample.obj_results)
+        top2 = logits.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4                             # ties within fp32 noise may go either way
+        assert clear.float().mean() > 0.99
+        assert np.array_equal(lab["labels"][clear.numpy()], logits.argmax(1).float().numpy()[clear.numpy()])
 
 
 def test_label_out_without_classifier_raises_like_reference(dev, tmp_path):

@@ -1,15 +1,37 @@
-"""Tensor-core packing + fp16x3 precision, validated on the CPU against the reference's golden fields."""
+"""Tensor-core packing + split-precision arithmetic of csrc/k1_tc.cu, validated on the CPU against the
+reference's golden fields (emulated from the packed bytes; the GPU tests pin the kernel to the emulator)."""
 import numpy as np
 import pytest
 
-from alignsdf_b200 import packer, tc_pack
+from alignsdf_b200 import engine, packer, tc_pack
 from oracle import alignsdf_oracle as orc
 from tests import helpers
 from tests.tc_emulate import emulate
 
+ENGINEERED = ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_obj6_n12"]
+PLAIN = ["sep_plain_g1_n32", "sep_plain_g4_n32", "sep_plain_g16_n32", "sep_default_n32"]
+COMBINED = ["comb_both9_n16", "comb_plain_g4_n24", "comb_default_n16"]
+
+
+def _emulated_errors(name, kind, n_points, seed=1):
+    meta, g, dec, sample = helpers.load_case(name)
+    topo = packer.decoder_topology(dec)
+    assert tc_pack.supported(topo)
+    raw, scales = tc_pack.pack_static_numpy(topo, kind)
+    br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
+    samp, info = tc_pack.pack_sample_numpy(br, scales, 2.0, kind)
+    N = meta["N"]
+    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
+    sel = np.random.default_rng(seed).choice(N ** 3, min(n_points, N ** 3), replace=False)
+    (hand, obj), vmax = emulate(raw, samp, xyz[sel], kind, len(topo.branches), want_max=True)
+    eh = np.abs(hand - g["pass1_hand"].reshape(-1)[sel]).max()
+    eo = np.abs(obj - g["pass1_obj"].reshape(-1)[sel]).max()
+    rng = max(np.abs(g["pass1_hand"]).max(), np.abs(g["pass1_obj"]).max())
+    return float(max(eh, eo)), float(rng), vmax, (hand, obj)
+
 
 def test_swizzle_roundtrip_and_pattern():
-    m = np.arange(128 * 64, dtype=np.float32).reshape(128, 64).astype(np.float16)
+    m = np.arange(64 * 64, dtype=np.float32).reshape(64, 64).astype(np.float16)
     flat = tc_pack.swizzle_tile(m)
     assert np.array_equal(tc_pack.unswizzle_tile(flat), m)
     # row 0 is stored unswizzled; in row 1 the 16-byte chunks 0 and 1 swap places
@@ -19,87 +41,102 @@ def test_swizzle_roundtrip_and_pattern():
     assert np.array_equal(flat[512:576], m[8])
 
 
-@pytest.mark.parametrize("name", ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_obj6_n12"])
-def test_emulated_kernel_matches_reference_golden(name):
-    """fp16x3 split precision + packing order, pass-1 field vs the real reference: <= 1e-5
-    (measured ~1e-6 and below)."""
-    meta, g, dec, sample = helpers.load_case(name)
-    topo = packer.decoder_topology(dec)
-    assert tc_pack.supported(topo)
-    raw, scales, hs = tc_pack.pack_static_numpy(topo)
-    br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
-    samp = tc_pack.pack_sample_numpy(br)
-    N = meta["N"]
-    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
-    sel = np.random.default_rng(0).choice(N ** 3, 1500, replace=False)
-    hand, obj = emulate(raw, samp, xyz[sel])
-    eh = np.abs(hand - g["pass1_hand"].reshape(-1)[sel]).max()
-    eo = np.abs(obj - g["pass1_obj"].reshape(-1)[sel]).max()
-    assert eh <= 1e-5 and eo <= 1e-5, (eh, eo)
-    assert eh <= 2e-6 and eo <= 2e-6, (eh, eo)      # the margin the design relies on
-
-
-def test_unsupported_topologies_are_routed_to_the_generic_kernel():
-    for name in ("comb_both9_n16", "comb_cls_n12"):
-        meta, g, dec, sample = helpers.load_case(name)
-        assert not tc_pack.supported(packer.decoder_topology(dec))
-
-
-@pytest.mark.parametrize("name", ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_obj6_n12"])
-def test_emulated_v2_kernel_matches_reference_golden(name):
-    """k1_tc2.cu arithmetic (A_hi in TMEM, bias/point terms as K=16 products) emulated from the packed
-    bytes vs the real reference: <= 1e-5 (measured ~1e-6)."""
-    from alignsdf_b200 import tc2_pack
-    from tests.tc2_emulate import emulate as emulate2
-    meta, g, dec, sample = helpers.load_case(name)
-    topo = packer.decoder_topology(dec)
-    raw, scales = tc2_pack.pack_static_numpy(topo)
-    br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
-    samp, info = tc2_pack.pack_sample_numpy(br, scales)
-    N = meta["N"]
-    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
-    sel = np.random.default_rng(1).choice(N ** 3, 1200, replace=False)
-    hand, obj = emulate2(raw, samp, xyz[sel])
-    eh = np.abs(hand - g["pass1_hand"].reshape(-1)[sel]).max()
-    eo = np.abs(obj - g["pass1_obj"].reshape(-1)[sel]).max()
-    assert eh <= 1e-5 and eo <= 1e-5, (eh, eo, info)
-    assert eh <= 3e-6 and eo <= 3e-6, (eh, eo, info)
-
-
 def test_e4m3_codec_and_fp8_tile_swizzle():
-    from alignsdf_b200 import tc3_pack
     b = np.arange(256, dtype=np.uint8)
-    v = tc3_pack.e4m3_decode(b)
+    v = tc_pack.e4m3_decode(b)
     ok = np.isfinite(v)
     assert ok.sum() == 254 and np.abs(v[ok]).max() == 448.0
-    assert np.array_equal(tc3_pack.e4m3_encode(v[ok]), b[ok])     # every finite code round-trips
-    assert tc3_pack.e4m3_decode(tc3_pack.e4m3_encode(np.array([448.0, 1e9, -1e9, 0.0625, 2.0 ** -9])).view(np.uint8)).tolist() == \
+    assert np.array_equal(tc_pack.e4m3_encode(v[ok]), b[ok])     # every finite code round-trips
+    assert tc_pack.e4m3_decode(tc_pack.e4m3_encode(np.array([448.0, 1e9, -1e9, 0.0625, 2.0 ** -9])).view(np.uint8)).tolist() == \
         [448.0, 448.0, -448.0, 0.0625, 2.0 ** -9]
     m = np.random.default_rng(0).integers(0, 256, (64, 128)).astype(np.uint8)
-    flat = tc3_pack.swizzle_tile8(m)
-    assert np.array_equal(tc3_pack.unswizzle_tile8(flat), m)
+    flat = tc_pack.swizzle_tile8(m)
+    assert np.array_equal(tc_pack.unswizzle_tile8(flat), m)
     assert np.array_equal(flat[:128], m[0])                      # row 0 is stored unswizzled
     assert np.array_equal(flat[128:144], m[1, 16:32]) and np.array_equal(flat[144:160], m[1, 0:16])
     assert np.array_equal(flat[1024:1152], m[8])                 # rows 8..15 start 1024 B later
 
 
-@pytest.mark.parametrize("name", ["sep_both9_n24", "sep_nerf3_n16", "sep_hand51_n16", "sep_obj6_n12"])
-def test_emulated_v3_kernel_matches_reference_golden(name):
-    """k1_tc3.cu arithmetic (fp16 main product, e4m3 correction products) emulated from the packed bytes
-    vs the real reference: <= 1e-5 (measured 2.3e-6), activations far inside the fp8 operand range."""
-    from alignsdf_b200 import tc3_pack
-    from tests.tc3_emulate import emulate as emulate3
+def test_topologies_the_tensor_core_kernel_accepts():
+    for name in ENGINEERED + PLAIN + COMBINED:
+        assert tc_pack.supported(packer.decoder_topology(helpers.load_case(name)[2])), name
+    # xyz_in_all, LayerNorm and NeRF-encoded decoders run on the generic kernel
+    for name in ("comb_xyzall_n12", "sep_ln_both9_n12", "comb_ln_both9_n12"):
+        assert not tc_pack.supported(packer.decoder_topology(helpers.load_case(name)[2])), name
+
+
+@pytest.mark.parametrize("name", ENGINEERED + PLAIN)
+def test_emulated_f16x3_kernel_matches_reference_golden(name):
+    """All three products in fp16, emulated from the packed bytes vs the real reference: inside the 1e-5 contract
+    for EVERY decoder, engineered or not (error ~2.5e-6 x output range; at last-layer gain 16 the reference's own
+    fp32 evaluation is only reproducible to 4.5e-6, oracle/make_golden.py)."""
+    err, rng, _, _ = _emulated_errors(name, tc_pack.F16X3, 1200)
+    assert err <= 1e-5, (name, err, rng)
+    assert err <= 3e-6 + 7e-6 * min(rng, 1.0), (name, err, rng)
+
+
+@pytest.mark.parametrize("name", ENGINEERED + ["sep_default_n32"])
+def test_emulated_f16_f8_kernel_on_decoders_it_is_valid_for(name):
+    """fp16 main product + e4m3 corrections: fine on the engineered decoders and on torch's default initialisation
+     -- measured <= 2.3e-6 -- with activations far inside the fp8 operand range."""
+    err, rng, vmax, _ = _emulated_errors(name, tc_pack.F16_F8, 1200)
+    assert err <= 4e-6, (name, err, rng)
+    assert vmax < tc_pack.FP8_LIMIT / 8
+
+
+@pytest.mark.parametrize("name,inside", [("sep_both9_n24", True), ("sep_default_n32", True), ("sep_plain_g1_n32", False),
+                                         ("sep_plain_g4_n32", False), ("sep_plain_g16_n32", False)])
+def test_calibration_rule_separates_the_decoders_f16_f8_is_valid_for(name, inside):
+    """the e4m3 corrections leave ~1e-4 x output range on plain random decoders (1e-5 .. 1.7e-4,
+    outside the contract).  The engine's rule -- max |F16_F8 - F16X3| over random points of the cube <= CALIB_TOL --
+    accepts exactly the decoders on which F16_F8 is safe."""
+    e8, rng, _, o8 = _emulated_errors(name, tc_pack.F16_F8, 1500, seed=5)
+    e16, _, _, o16 = _emulated_errors(name, tc_pack.F16X3, 1500, seed=5)
+    calib = max(np.abs(o8[0] - o16[0]).max(), np.abs(o8[1] - o16[1]).max())
+    if inside:
+        assert calib <= engine.CALIB_TOL and e8 <= 4e-6, (name, calib, e8)
+    else:
+        assert calib > engine.CALIB_TOL, (name, calib, e8)        # rejected -> the engine uses F16X3
+        assert e16 <= 1e-5, (name, e16)
+    if name in ("sep_plain_g4_n32", "sep_plain_g16_n32"):
+        assert e8 > 1e-5, (name, e8)                              # ... and rightly so
+
+
+@pytest.mark.parametrize("name", COMBINED)
+@pytest.mark.parametrize("kind", [tc_pack.F16X3, tc_pack.F16_F8])
+def test_emulated_combined_decoder(name, kind):
+    """CombinedDecoder: one MLP, both outputs from the same layer-3 accumulators (w4 rows 0 / 1)."""
+    err, rng, _, _ = _emulated_errors(name, kind, 1000)
+    if kind == tc_pack.F16X3:
+        assert err <= 3e-6 + 7e-6 * min(rng, 1.0), (name, err, rng)
+    elif name != "comb_plain_g4_n24":
+        assert err <= 4e-6, (name, err, rng)
+
+
+@pytest.mark.parametrize("name", ["sep_both9_n24", "sep_hand51_n16", "sep_obj6_n12", "comb_both9_n16"])
+def test_bind_static_arrays_reproduce_the_host_fold(name):
+    """The float64 arrays csrc/bind.cu folds a sample from (latent / feature columns of layers 0 and 2, biases)
+    give the same M, B as packer.fold_decoder when contracted the way the kernel does."""
     meta, g, dec, sample = helpers.load_case(name)
     topo = packer.decoder_topology(dec)
-    raw, scales = tc3_pack.pack_static_numpy(topo)
+    arr = tc_pack.bind_static_numpy(topo)
+    L, nd = topo.latent_size, len(topo.branches)
+    per = 2 * 512 * L + 2 * 512 * tc_pack.MAX_POINT_DIM + 4 * 512
+    assert arr.size == nd * per
+    A, c = packer.embedding_affine(sample.specs, sample.mano_results, sample.obj_results)
+    z = sample.latent.double().numpy().reshape(-1)
     br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
-    samp, info = tc3_pack.pack_sample_numpy(br, scales)
-    N = meta["N"]
-    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
-    sel = np.random.default_rng(1).choice(N ** 3, 1200, replace=False)
-    (hand, obj), vmax = emulate3(raw, samp, xyz[sel], want_max=True)
-    eh = np.abs(hand - g["pass1_hand"].reshape(-1)[sel]).max()
-    eo = np.abs(obj - g["pass1_obj"].reshape(-1)[sel]).max()
-    assert eh <= 1e-5 and eo <= 1e-5, (eh, eo, info)
-    assert eh <= 4e-6 and eo <= 4e-6, (eh, eo, info)
-    assert vmax < tc3_pack.FP8_LIMIT / 8
+    for d, (tag, _) in enumerate(topo.branches):
+        blk = arr[d * per:(d + 1) * per]
+        wz = blk[:2 * 512 * L].reshape(2, 512, L)
+        wf = blk[2 * 512 * L:2 * 512 * L + 2 * 512 * 64].reshape(2, 512, 64)
+        b = blk[2 * 512 * L + 2 * 512 * 64:].reshape(4, 512)
+        idx = packer.branch_feature_index(topo, tag)
+        for j, l in ((0, 0), (1, 2)):
+            M = wf[j][:, :len(idx)] @ A[idx]
+            B = b[l] + wz[j] @ z + wf[j][:, :len(idx)] @ c[idx]
+            assert np.abs(M - br[d].layers[l].M).max() <= 1e-6 * max(1.0, np.abs(M).max())
+            assert np.abs(B - br[d].layers[l].B).max() <= 1e-6 * max(1.0, np.abs(B).max())
+        h = br[d].layers[1].B.shape[0]
+        assert np.array_equal(b[1, :h].astype(np.float32), br[d].layers[1].B) and not b[1, h:].any()
+        assert np.array_equal(b[3].astype(np.float32), br[d].layers[3].B)
