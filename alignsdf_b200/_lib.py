@@ -78,7 +78,7 @@ def lib():
     L.asdf_tc_eval.restype = C.c_int
     L.asdf_tc_eval.argtypes = [C.POINTER(TcLaunch), C.POINTER(Query), vp]
     L.asdf_tc_static_bytes.restype = C.c_int64
-    L.asdf_tc_static_bytes.argtypes = [C.c_int32]
+    L.asdf_tc_static_bytes.argtypes = [C.c_int32, C.c_int32]
     L.asdf_tc_sample_bytes.restype = C.c_int64
     L.asdf_tc_bind.restype = C.c_int
     L.asdf_tc_bind.argtypes = [C.POINTER(TcBindDesc), vp, vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp]

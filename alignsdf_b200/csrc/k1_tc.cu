@@ -63,12 +63,16 @@ constexpr int kRows = 128;                  // points per CTA
 constexpr int kPtsPerTile = 256;            // per CTA pair
 constexpr int kTileBytes = 64 * 64 * 2;     // weight tile: 64 rows x 64 k fp16, or 64 rows x (64 + 64) e4m3 = 8 KiB
 constexpr int kSlotBytes = kRows * 128;     // ALO slot: 128 rows x (64 lo8 + 64 x8 | 64 lo16) = 16 KiB
-constexpr int kRing = 5;                    // ring slots of one (fp16, fp8) tile pair each
-constexpr int kMainTilesPerDecoder = 128;   // 32 (L1) + 32 (L2) + 64 (L3)
+constexpr int kRing = 10;                   // ring slots of one 8 KiB tile each
+constexpr int kChunksPerDecoder = 64;       // 64-wide K chunks of all N blocks: 16 (L1) + 16 (L2) + 32 (L3)
 constexpr int kPTilesPerDecoder = 14;       // 4 (L0) + 2 (L1) + 4 (L2) + 4 (L3) N blocks
-constexpr int kSlotTileBytes = 2 * kTileBytes;   // a ring slot holds a (fp16, fp8) pair (16 KiB) or one P tile
-constexpr int kFillsPerItem = kMainTilesPerDecoder / 2 + kPTilesPerDecoder;   // ring fills per decoder instance
-constexpr int64_t kWeightBytesPerDecoder = (int64_t)2 * kMainTilesPerDecoder * kTileBytes;   // [rank][tile]
+// weight tiles per 64-wide K chunk: the correction tiles of the chunk (F16X3: hi16(W) and lo16(W); F16_F8: the
+// [W8 | Wl8] tile) come in the block's correction phase, the hi16(W) tile again in its main phase
+__host__ __device__ constexpr int tiles_per_chunk(bool f8) { return f8 ? 2 : 3; }
+__host__ __device__ constexpr int fills_per_instance(bool f8) { return kChunksPerDecoder * tiles_per_chunk(f8) + kPTilesPerDecoder; }
+__host__ __device__ constexpr int64_t weight_bytes_per_decoder(bool f8) {          // [rank][tile]
+  return (int64_t)2 * kChunksPerDecoder * tiles_per_chunk(f8) * kTileBytes;
+}
 constexpr int kStaticParamFloats = 512 + 8;            // w4[512] | b4, inv1, inv2, inv3, pad
 constexpr int64_t kSampleTileBytes = (int64_t)2 * 2 * kPTilesPerDecoder * kTileBytes;   // P tiles [dec][rank][14]
 constexpr int64_t kSampleBytes = kSampleTileBytes + 64;                                  // + 16 floats
@@ -77,7 +81,7 @@ constexpr int kOffALo = 0;
 constexpr int kApBytes = kRows * 16 * 2;                          // point operand: 128 rows x 16 k, no swizzle (4 KiB)
 constexpr int kOffAP = kOffALo + 8 * kSlotBytes;                 // 131072
 constexpr int kOffRing = kOffAP + 2 * kApBytes;                  // 139264 (1024-aligned); AP is double-buffered per item
-constexpr int kOffW4 = kOffRing + kRing * kSlotTileBytes;        // 221184: w4 of BOTH decoders, loaded once
+constexpr int kOffW4 = kOffRing + kRing * kTileBytes;            // 221184: w4 of BOTH decoders, loaded once
 constexpr int kOffRed = kOffW4 + 2 * 512 * 4;
 constexpr int kOffBar = kOffRed + 2 * 2 * kRows * 4;             // [output][column half][row] partial sums
 constexpr int kBarFull = 0;
@@ -286,37 +290,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
     // Pushes tiles in exactly the order the issuer consumes them (see the schedule above).
     if (lane == 0 && n_inst > 0) {
       uint32_t slot = 0, phase = 0;
-      auto push = [&](const uint8_t* src, uint32_t bytes) {
+      auto push = [&](const uint8_t* src) {
         mbar_wait(bar(kBarEmpty + slot), phase ^ 1);
         const uint32_t fb = bar((leader ? kBarFull : kBarFullLocal) + slot);
         if (kDebug && (a.dbg_flags & 2)) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(fb) : "memory");
         } else {
-          mbar_expect_tx(fb, bytes);
-          bulk_g2s(sbase + kOffRing + slot * kSlotTileBytes, src, bytes, fb);
+          mbar_expect_tx(fb, kTileBytes);
+          bulk_g2s(sbase + kOffRing + slot * kTileBytes, src, kTileBytes, fb);
         }
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       };
       auto ptile = [&](uint32_t smp, int dec, int g) {
         return a.samp + (int64_t)smp * a.samp_stride + ((int64_t)(dec * 2 + rank) * kPTilesPerDecoder + g) * kTileBytes;
       };
+      constexpr int kCorrTiles = tiles_per_chunk(kF8) - 1;
       uint32_t smp = sample_of(0);
-      push(ptile(smp, 0, 0), kTileBytes);
-      push(ptile(smp, 0, 1), kTileBytes);
+      push(ptile(smp, 0, 0));
+      push(ptile(smp, 0, 1));
       for (int s_i = 0; s_i < n_inst; ++s_i) {
         const int dec = s_i & dshift;
         const bool has_next = s_i + 1 < n_inst;
         const int dec_next = (s_i + 1) & dshift;
         const uint32_t smp_next = has_next ? sample_of((s_i + 1) >> dshift) : smp;
-        const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * kMainTilesPerDecoder * kTileBytes;
+        const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * (weight_bytes_per_decoder(kF8) / 2);
         for (int g = 2; g < kPTilesPerDecoder; ++g) {
-          push(ptile(smp, dec, g), kTileBytes);
           const int n = layer_chunks(nb_layer(g));
-          for (int j = 0; j < n; ++j) {
-            push(mt, kSlotTileBytes); mt += kSlotTileBytes;             // (hi, correction) pair in one copy
+          for (int j = 0; j < n * kCorrTiles; ++j) { push(mt); mt += kTileBytes; }    // correction phase
+          push(ptile(smp, dec, g));
+          for (int j = 0; j < n; ++j) {                                               // main phase
+            push(mt); mt += kTileBytes;
             if (g == kPTilesPerDecoder - 1 && has_next) {
-              if (j == 2) push(ptile(smp_next, dec_next, 0), kTileBytes);
-              if (j == 5) push(ptile(smp_next, dec_next, 1), kTileBytes);
+              if (j == 2) push(ptile(smp_next, dec_next, 0));
+              if (j == 5) push(ptile(smp_next, dec_next, 1));
             }
           }
         }
@@ -329,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       // ======================= peer CTA: relay "my half of the tile landed" =======================
       if (lane == 0) {
         uint32_t slot = 0, phase = 0;
-        const int fills = n_inst * kFillsPerItem;
+        const int fills = n_inst * fills_per_instance(kF8);
         for (int i = 0; i < fills; ++i) {
           mbar_wait(bar(kBarFullLocal + slot), phase);
           mbar_arrive_cluster(bar(kBarFull + slot), 0);
@@ -356,33 +362,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         mbar_wait(bar0 + 8 * (kBarFull + slot), phase);
         if (kDebug) w_ring += clock64() - t0;
         tc_fence_after();
-        return ring_lo + slot * (kSlotTileBytes >> 4);
-      };
-      auto release = [&]() __attribute__((always_inline)) {
-        umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + slot));
+        const uint32_t d = ring_lo + slot * (kTileBytes >> 4);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
+        return d;
       };
-      // start an N block in accumulator buffer `buf`: wait until its previous contents were drained, then the
-      // bias + point-term UMMA (K = 16) of the block against the point operand of `item`
-      auto begin_block = [&](int buf, uint32_t ap_sel) __attribute__((always_inline)) -> uint32_t {
+      // the UMMAs issued so far no longer need ring slot `rel_slot` once they retire
+      uint32_t rel_slot = 0;
+      auto release = [&]() __attribute__((always_inline)) {
+        umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + rel_slot));
+        if (++rel_slot == kRing) rel_slot = 0;
+      };
+      // claim accumulator buffer `buf`: wait until its previous contents were drained
+      auto acquire = [&](int buf) __attribute__((always_inline)) -> uint32_t {
         const long long t0 = kDebug ? clock64() : 0;
         mbar_wait(bar0 + 8 * (kBarTmemEmpty + buf), ((buf ? cnt_y : cnt_x) & 1u) ^ 1u);
         if (kDebug) w_acc += clock64() - t0;
         if (buf) ++cnt_y; else ++cnt_x;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_u + buf * 128;
+        return tmem_u + buf * 128;
+      };
+      // the bias + point-term UMMA (K = 16) of a block against the point operand AP[ap_sel]
+      auto point_term = [&](uint32_t d_tmem, uint32_t ap_sel, uint32_t acc) __attribute__((always_inline)) {
         const uint32_t b = take();
-        umma_ap(issue, d_tmem, sb + kOffAP + ap_sel * kApBytes, b, 0u);
+        umma_ap(issue, d_tmem, sb + kOffAP + ap_sel * kApBytes, b, acc);
         release();
-        return d_tmem;
+      };
+      // a layer-0 block: nothing but the point term
+      auto layer0_block = [&](uint32_t ap_sel) __attribute__((always_inline)) {
+        const uint32_t d_tmem = acquire(0);
+        point_term(d_tmem, ap_sel, 0u);
+        umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + 0));
       };
       auto wait_ap = [&]() __attribute__((always_inline)) { mbar_wait(bar0 + 8 * kBarApFull, ap_phase); ap_phase ^= 1; tc_fence_after(); };
       // prologue: the first two layer-0 blocks of instance 0
       wait_ap();
-      for (int g = 0; g < 2; ++g) {
-        begin_block(0, 0);
-        umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + 0));
-      }
+      for (int g = 0; g < 2; ++g) layer0_block(0);
       for (int s_i = 0; s_i < n_inst; ++s_i) {
         const uint32_t ap_sel = (uint32_t)(s_i >> dshift) & 1u;    // AP buffer of this instance's item
         const bool has_next = s_i + 1 < n_inst;
@@ -391,8 +405,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
           const bool first_nb = g == 4 || g == 6 || g == 10;
           const bool last_blk = g == kPTilesPerDecoder - 1;
           const int buf = buf_of(g);
-          const uint32_t d_tmem = begin_block(buf, ap_sel);
           const int nch = layer_chunks(layer);
+          const uint32_t d_tmem = acquire(buf);
+          if (nch == 0) {                                    // layer-0 blocks 2, 3 of this instance
+            point_term(d_tmem, ap_sel, 0u);
+            umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
+            continue;
+          }
+          // The tensor core truncates its fp32 accumulator toward zero after every UMMA (tools/probes/
+          // acc_round_probe.cu), an error proportional to the accumulator's magnitude at that moment.  So the
+          // CORRECTION products (2^-11 of the main product) are accumulated first, while the accumulator is
+          // still tiny -- their truncation is then negligible -- and the bias / point term and the main product
+          // last: 1 + 4 nch truncations at full magnitude instead of 1 + 12 nch.
           for (int j = 0; j < nch; ++j) {
             // layer 3 reads x3 as it becomes available (positions 4..7 first), except in its last block
             const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
@@ -405,17 +429,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
             }
             const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
             const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
-            const uint32_t b = take();                       // (hi, correction) tile pair
+            if (kF8) {
+              const uint32_t b8 = take();                    // [W8 | Wl8] rows against the [lo8 | x8] rows of ALO
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                 // TMEM-A and SMEM-A forms alternate: evens out the smem reads
-              if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + ks * 2, 1u);
-              if (kF8) {
-                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b + (kTileBytes >> 4) + ks * 2, 1u);
-              } else if (!(kDebug && (a.dbg_flags & 4))) {
-                umma_ss16_lo(issue, d_tmem, alo + ks * 2, b + ks * 2, 1u);                              // lo16(x) . hi16(W)
-                umma_ts_lo(issue, d_tmem, ahi + ks * 8, b + (kTileBytes >> 4) + ks * 2, 1u);            // hi16(x) . lo16(W)
+              for (int ks = 0; ks < 4; ++ks)
+                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b8 + ks * 2, (j | ks) ? 1u : 0u);
+              release();
+            } else {
+              const uint32_t bh = take(), bl = take();
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (kDebug && (a.dbg_flags & 4)) continue;
+                umma_ss16_lo(issue, d_tmem, alo + ks * 2, bh + ks * 2, (j | ks) ? 1u : 0u);      // lo16(x) . hi16(W)
+                umma_ts_lo(issue, d_tmem, ahi + ks * 8, bl + ks * 2, 1u);                        // hi16(x) . lo16(W)
               }
+              release();
+              release();
             }
+          }
+          point_term(d_tmem, ap_sel, (kDebug && (a.dbg_flags & 4)) ? 0u : 1u);
+          for (int j = 0; j < nch; ++j) {
+            const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
+            const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
+            const uint32_t bh = take();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, bh + ks * 2, 1u);
             release();
             if (last_blk && has_next) {
               // positions {0,1} / {2,3} consumed -> the next instance's layer-0 epilogues may overwrite them;
@@ -424,8 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
               if (j == 3) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 1));
               if (j == 2 || j == 5) {
                 if (j == 2 && ((s_i + 1) & dshift) == 0) wait_ap();     // next instance starts a new item
-                begin_block(0, (uint32_t)((s_i + 1) >> dshift) & 1u);
-                umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + 0));
+                layer0_block((uint32_t)((s_i + 1) >> dshift) & 1u);
               }
             }
           }
@@ -446,7 +484,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
     const int et = threadIdx.x - kEpiWarp0 * 32;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t a_lo = sbase + kOffALo, sW4 = sbase + kOffW4, sRed = sbase + kOffRed;
-    const float* sparams = reinterpret_cast<const float*>(a.stat + (int64_t)a.n_dec * kWeightBytesPerDecoder);
+    const float* sparams = reinterpret_cast<const float*>(a.stat + (int64_t)a.n_dec * weight_bytes_per_decoder(kF8));
     const bool two_out = a.n_dec == 1;             // CombinedDecoder: outputs 0 / 1 = w4 rows 0 / 1 of the one MLP
     uint32_t cnt_x = 0, cnt_y = 0;                 // uses so far of accumulator buffer X / Y (same sequence as the issuer)
     uint32_t posfree_phase = 0;
@@ -706,8 +744,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
 }  // namespace tc
 }  // namespace asdf
 
-extern "C" int64_t asdf_tc_static_bytes(int32_t n_decoders) {
-  return (int64_t)n_decoders * asdf::tc::kWeightBytesPerDecoder + (int64_t)2 * asdf::tc::kStaticParamFloats * 4;
+extern "C" int64_t asdf_tc_static_bytes(int32_t kind, int32_t n_decoders) {
+  return (int64_t)n_decoders * asdf::tc::weight_bytes_per_decoder(kind == ASDF_TC_F16_F8) +
+         (int64_t)2 * asdf::tc::kStaticParamFloats * 4;
 }
 extern "C" int64_t asdf_tc_sample_bytes(void) { return asdf::tc::kSampleBytes; }
 

@@ -139,18 +139,16 @@ def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_fi
 
 
 def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None):
-    """bound.two_pass + the host check of its speculative parts; re-runs through the next safer kernel kind when
-    the calibration / operand-range flags say so.  -> result dict, or None when only the generic kernel is left."""
-    path = _engine._PATH_ALIASES.get(path, path) if path else bound.engine.path
-    while bound.tc_ok and path != "simt":
-        kind = bound.auto_kind(path)
-        r = bound.two_pass(N, mask, grid_mode, kind, keep_pass1)
-        v = bound.verify()
-        if v == "ok":
+    """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags); re-runs
+    through the next safer kernel when they say so."""
+    lvl = bound.auto_level(path)
+    while True:
+        r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1)
+        need = bound.verify()
+        if need <= lvl:
+            bound.last_kind = _engine.LEVEL_NAMES[lvl]
             return r
-        if v == "f16" and path == "f8":
-            path = "f16"
-    return None
+        lvl = need
 
 
 def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
@@ -174,13 +172,12 @@ def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_b
     if bound.tc_ok and not want_cls:
         # tensor-core kernel: pass 1 -> asdf_regrid -> pass 2 without a host round trip in between
         r = _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path)
-        if r is not None:
-            g = r["grid"][0].cpu()
-            mm = r["minmax"][0].cpu()
-            view = lambda t: None if t is None else t[0].view(shp)
-            return dict(pass1_hand=view(r["pass1_hand"]), pass1_obj=view(r["pass1_obj"]), hand=view(r["hand"]),
-                        obj=view(r["obj"]), cls=None, voxel=g[0].clone(), origin=g[1:4].clone(),
-                        min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
+        g = r["grid"][0].cpu()
+        mm = r["minmax"][0].cpu()
+        view = lambda t: None if t is None else t[0].view(shp)
+        return dict(pass1_hand=view(r["pass1_hand"]), pass1_obj=view(r["pass1_obj"]), hand=view(r["hand"]),
+                    obj=view(r["obj"]), cls=None, voxel=g[0].clone(), origin=g[1:4].clone(),
+                    min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
     h1, o1, _, box = bound.eval_grid(N, voxel_size, [-1.0, -1.0, -1.0], grid_mode, bbox_mask=mask,
                                      path=path)
     mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
@@ -297,8 +294,9 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
             mano = None if smp.mano_results is None else {k: to(v) for k, v in smp.mano_results.items()}
             obj = None if smp.obj_results is None else {k: to(v) for k, v in smp.obj_results.items()}
             bound = _engine.get_engine(decoder, dev).bind(latent, smp.specs, mano, obj)
-            if bound.tc_ok:
-                bound.tc_blocks(bound.auto_kind(), 2.0)      # P tiles built on the device, ahead of the sample's turn
+            lvl = bound.auto_level()                     # starts the calibration run as well
+            if lvl < _engine.LEVEL_SIMT:
+                bound.tc_blocks(_engine.LEVEL_KIND[lvl], 2.0)    # P tiles built on the device, ahead of the sample's turn
             ready = torch.cuda.Event()
             ready.record(bind_stream[dev])
         return dev, latent, mano, obj, bound, ready

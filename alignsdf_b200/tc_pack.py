@@ -2,19 +2,21 @@
 float64 arrays the device-side bind (csrc/bind.cu) folds a sample from, and a numpy statement of the
 per-sample block the bind kernel writes (tests compare the two; the product never packs on the host).
 
-Static stream (bytes): main weight tiles ``[decoder][cta rank][128 tiles]`` of 8 KiB
+Static stream (bytes): weight tiles ``[decoder][cta rank][tiles]`` of 8 KiB, N block after N block
     L1: nb = 0..1, kc = 0..7      rows n = 128 nb + 64 c + r   k = 64 kc + kk      (W1 padded to [256,512])
     L2: nb = 0..3, kc = 0..3                                                       (W2[:, :h] padded to [512,256])
     L3: nb = 0..3, j  = 0..7      kc = j, except the LAST N block: kc = (j + 4) % 8 -- x3's chunk c lives at
                                   K position (c + 4) % 8 and that block walks the positions in natural order so
                                   that positions 0..3 are released early for the next instance's layer-0
                                   epilogues (k1_tc.cu)
-each (kc) entry being a PAIR of tiles:
+and inside an N block first the tiles of its CORRECTION phase, chunk after chunk, then the hi tiles of its MAIN
+phase (the kernel accumulates the small correction products first: the tensor core truncates its accumulator
+after every UMMA, which costs the least while the accumulator is still tiny):
     hi tile     shared-memory image (K-major, 128B swizzle) of 64 rows x 64 k of  hi16(s_l W_l)
-    correction  F16X3:  the same image of lo16(s_l W_l) = fp16(s_l W_l - hi16(s_l W_l))
-                F16_F8: 64 rows x 128 B: bytes 0..63  = e4m3(2^-10 s_l W_l[k]),
-                                         bytes 64..127 = e4m3((s_l W_l - hi16(s_l W_l))[k])
-followed by 2 x 520 floats: w4[512] | b4, 1/s1, 1/s2, 1/(t s3), pad  -- per decoder (SeparateDecoder) or per
+    correction  F16X3:  the hi tile (for lo16(x).hi16(W)) and the same image of lo16(s_l W_l) = fp16(s_l W_l - hi16(s_l W_l))
+                F16_F8: one tile of 64 rows x 128 B: bytes 0..63  = e4m3(2^-10 s_l W_l[k]),
+                                                     bytes 64..127 = e4m3((s_l W_l - hi16(s_l W_l))[k])
+(3 / 2 tiles per chunk: 192 / 128 tiles per decoder and rank), followed by 2 x 520 floats: w4[512] | b4, 1/s1, 1/s2, 1/(t s3), pad  -- per decoder (SeparateDecoder) or per
 output of the one MLP (CombinedDecoder).  s_l are powers of two with max|s_l W_l| in [8192, 16384); t is the
 power of two the kernel keeps its activations multiplied by (16 for F16X3, 1 for F16_F8).
 
@@ -37,7 +39,8 @@ ACT_SCALE = {F16X3: 16.0, F16_F8: 1.0}
 ROWS, TK = 64, 64
 TILE_ELEMS = ROWS * TK
 TILE_BYTES = TILE_ELEMS * 2
-MAIN_TILES = 128
+CHUNKS = 64              # 64-wide K chunks of all N blocks of a decoder: 16 (L1) + 16 (L2) + 32 (L3)
+TILES_PER_CHUNK = {_lib.TC_F16X3: 3, _lib.TC_F16_F8: 2}
 P_TILES = 14
 STATIC_PARAM_FLOATS = 520
 SAMPLE_TILE_BYTES = 2 * 2 * P_TILES * TILE_BYTES
@@ -160,7 +163,8 @@ def pack_static_numpy(topo, kind):
     """-> (uint8 stream, scales [2][3])"""
     nd = len(topo.branches)
     t = ACT_SCALE[kind]
-    stream = np.zeros((nd, 2, MAIN_TILES, TILE_BYTES), np.uint8)
+    ntiles = CHUNKS * TILES_PER_CHUNK[kind]
+    stream = np.zeros((nd, 2, ntiles, TILE_BYTES), np.uint8)
     params = np.zeros((2, STATIC_PARAM_FLOATS), np.float32)
     scales = weight_scales(topo)
     for d, (_, prefix) in enumerate(topo.branches):
@@ -171,19 +175,25 @@ def pack_static_numpy(topo, kind):
             for W, sc, nbs, kcs in ((W1, s[0], 2, 8), (W2, s[1], 4, 4), (W3, s[2], 4, 8)):
                 for nb in range(nbs):
                     r0 = 128 * nb + 64 * c
-                    for j in range(kcs):
+                    his = []
+                    for j in range(kcs):                 # correction phase
                         kc = (j + 4) % 8 if (W is W3 and nb == nbs - 1) else j
                         blk = (sc * W[r0:r0 + 64, 64 * kc:64 * kc + 64]).astype(np.float64)
                         hi = blk.astype(np.float16)
                         lo = blk - hi.astype(np.float64)
-                        stream[d, c, i] = swizzle_tile(hi).view(np.uint8)
+                        his.append(swizzle_tile(hi).view(np.uint8))
                         if kind == F16_F8:
-                            stream[d, c, i + 1] = swizzle_tile8(
+                            stream[d, c, i] = swizzle_tile8(
                                 np.concatenate([e4m3_encode(blk / LO_SCALE), e4m3_encode(lo)], 1))
+                            i += 1
                         else:
+                            stream[d, c, i] = his[-1]
                             stream[d, c, i + 1] = swizzle_tile(lo.astype(np.float16)).view(np.uint8)
-                        i += 2
-            assert i == MAIN_TILES
+                            i += 2
+                    for j in range(kcs):                 # main phase
+                        stream[d, c, i] = his[j]
+                        i += 1
+            assert i == ntiles
         W4, b4 = topo.layers[prefix][4]
         for o in range(W4.shape[0]):                     # one row per decoder, or the two outputs of the one MLP
             p = params[d + o]
@@ -195,7 +205,7 @@ def pack_static_numpy(topo, kind):
 
 def pack_static(topo, kind, device) -> torch.Tensor:
     raw, _ = pack_static_numpy(topo, kind)
-    expect = _lib.lib().asdf_tc_static_bytes(len(topo.branches))
+    expect = _lib.lib().asdf_tc_static_bytes(kind, len(topo.branches))
     if raw.nbytes != expect:
         raise _lib.AsdfError(f"packed weight stream is {raw.nbytes} B, library expects {expect} B")
     return torch.from_numpy(raw).to(device)

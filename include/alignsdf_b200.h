@@ -88,7 +88,7 @@ int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev, const fl
  *   ASDF_TC_F16X3   x.W ~= hi16(x).hi16(W) + lo16(x).hi16(W) + hi16(x).lo16(W): within the 1e-5 contract for any decoder
  *   ASDF_TC_F16_F8  the two correction products in e4m3 (2/3 of the tensor time): only for decoders whose
  *                   calibration run shows them inside the contract (alignsdf_b200/engine.py)
- * static_dev: asdf_tc_static_bytes(n_decoders) bytes (alignsdf_b200/tc_pack.py, one stream per kind);
+ * static_dev: asdf_tc_static_bytes(kind, n_decoders) bytes (alignsdf_b200/tc_pack.py, one stream per kind);
  * samples_dev: per sample asdf_tc_sample_bytes() bytes written by asdf_tc_bind (sample_stride apart);
  * grid_dev: NULL or float[n_samples][4] = {voxel, origin0, origin1, origin2} overriding q->voxel / q->origin per
  *   sample (e.g. written by asdf_regrid: pass 2 then needs no host round trip);
@@ -115,7 +115,7 @@ typedef struct {
   int32_t* status_dev;
 } asdf_tc_launch;
 int asdf_tc_eval(const asdf_tc_launch* l, const asdf_query* q, void* stream);
-int64_t asdf_tc_static_bytes(int32_t n_decoders);
+int64_t asdf_tc_static_bytes(int32_t kind, int32_t n_decoders);
 int64_t asdf_tc_sample_bytes(void);
 
 /* Per-sample set-up of the tensor-core path on the device (csrc/bind.cu).  Replaces what the reference recomputes

@@ -66,8 +66,8 @@ def test_device_bind_matches_the_numpy_statement(name, kind):
                 b = tc_pack.unswizzle_tile(wt[d, c, t]).astype(np.float64)[:, :16]
                 va, vb = a[:, 0:4] + a[:, 8:12], b[:, 0:4] + b[:, 8:12]          # hi + lo of (M, B)
                 assert np.array_equal(a[:, 4:7], a[:, 0:3]) and not a[:, 7].any() and not a[:, 12:].any()
-                scale = np.maximum(np.abs(vb), 1e-3)
-                assert (np.abs(va - vb) / scale).max() <= 2e-7, (d, c, t)
+                # one fp16 ulp of the lo half (the two float64 folds differ in summation order); subnormal lo: 2^-24
+                assert (np.abs(va - vb) <= 5e-7 * np.abs(vb) + 1.3e-7).all(), (d, c, t)
 
 
 def test_regrid_kernel_is_bit_equal_to_the_host_arithmetic():
@@ -94,12 +94,15 @@ def test_regrid_kernel_is_bit_equal_to_the_host_arithmetic():
                 assert float(v) == float(got[i, 0]) and torch.equal(o, got[i, 1:4]), (N, mask, i)
 
 
-@pytest.mark.parametrize("name", ENGINEERED + PLAIN)
+@pytest.mark.parametrize("name", ENGINEERED + ["sep_plain_g1_n32", "sep_plain_g4_n32", "sep_default_n32"])
 def test_f16x3_two_pass_fields_match_reference_golden(name):
-    """All-fp16 split precision: inside the contract for every decoder, engineered or not."""
+    """All-fp16 split precision: inside the contract up to |sdf| ~ 0.5 with margin, engineered decoder or not.
+    (At last-layer gain 16 it reaches 1.0e-5 .. 1.6e-5 -- two faithful fp32 evaluations differ by 4.5e-6 there --
+    which is why "auto" checks it against the fp32 kernel per sample: test_auto_path_*.)"""
     vols, g, _ = _volumes(name, "f16")
     assert vols["bound"].kinds_used == {"f16x3"}
-    _check_fields(vols, g)
+    worst = _check_fields(vols, g)
+    print(f"F16X3 {name}: max |sdf - reference| = {worst:.2e}")
 
 
 @pytest.mark.parametrize("name", ENGINEERED + ["sep_default_n32"])
@@ -114,25 +117,27 @@ def test_f16_f8_two_pass_fields_match_reference_golden(name):
 
 @pytest.mark.parametrize("name", ENGINEERED + PLAIN)
 def test_auto_path_picks_a_kernel_inside_the_contract(name):
-    """"auto" calibrates every sample (both kinds on 16 k random points, compared on the device) and
-    keeps the e4m3 kind only where the two agree to CALIB_TOL; whatever it picks is <= 1e-5 from the real reference."""
-    before = engine.STATS["f8_rejected"]
+    """"auto" calibrates EVERY sample -- exact-fp32 kernel vs the tensor-core kinds on 4 k random
+    points, compared on the device -- and uses the fastest kind that agrees to CALIB_TOL (else the fp32 kernel
+    itself); whatever it picks is <= 1e-5 from the real reference, engineered decoder or not."""
     vols, g, dec = _volumes(name, "auto")
-    eng = engine.get_engine(dec, DEV)
-    _check_fields(vols, g)
-    assert eng.calib["err"] is not None and eng.calib["samples"] >= 1
-    plain = name.startswith("sep_plain")
-    if plain:                                       # ~1e-4 x range with e4m3 corrections: rejected, sticky
-        assert eng.f8_ok is False and engine.STATS["f8_rejected"] == before + 1
-        assert eng.calib["err"] > engine.CALIB_TOL
-        # the volumes handed back were produced by the all-fp16 kind
+    bound = vols["bound"]
+    eng = bound.engine
+    worst = _check_fields(vols, g)
+    e8, e16 = bound.calib_err
+    print(f"auto {name}: {bound.last_kind}, calibration f8 {e8:.2e} f16 {e16:.2e}, max |sdf - reference| = {worst:.2e}")
+    assert eng.calib["samples"] >= 1
+    want = "f16+2xe4m3" if e8 <= engine.CALIB_TOL else ("f16x3" if e16 <= engine.CALIB_TOL else "simt")
+    assert bound.last_kind == want and eng.level == {"f16+2xe4m3": 0, "f16x3": 1, "simt": 2}[want]
+    if name in ENGINEERED + ["sep_default_n32"]:
+        assert want == "f16+2xe4m3"                 # benign / default-initialised decoders keep the fast kind
+    if name.startswith("sep_plain"):                # ~1e-4 x range with e4m3 corrections: rejected, sticky
+        assert want != "f16+2xe4m3" and e8 > engine.CALIB_TOL
         meta, _, _, sample = helpers.load_case(name)
         s = helpers.to_cuda(sample)
-        again = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], path="f16")
+        again = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"])
+        assert again["bound"].last_kind == want     # no second attempt at the rejected kind
         assert torch.equal(again["hand"], vols["hand"]) and torch.equal(again["obj"], vols["obj"])
-    else:
-        assert eng.f8_ok is True and eng.calib["err"] <= engine.CALIB_TOL
-        assert "f16+2xe4m3" in vols["bound"].kinds_used
 
 
 @pytest.mark.parametrize("kind,path,tol", [(tc_pack.F16X3, "f16", 3e-6), (tc_pack.F16_F8, "f8", 6e-6)])
@@ -176,15 +181,16 @@ def test_batched_launch_is_bit_identical_to_single_sample_launches(path):
     N = 20                                    # 8000 points: 32 tiles per sample, 160 items over 74 pairs (mixed samples per pair)
     kind = tc_pack.F16X3 if path == "f16" else tc_pack.F16_F8
     batch = eng.bind_batch([(s.latent, s.specs, s.mano_results, s.obj_results) for s in samples])
-    r = batch.two_pass(N, 3, "reference", kind, keep_pass1=True)
-    assert batch.verify() == "ok"
+    lvl = engine.LEVEL_F16 if path == "f16" else engine.LEVEL_F8
+    r = batch.two_pass(N, 3, "reference", lvl, keep_pass1=True)
+    assert batch.verify() <= lvl
     for i, s in enumerate(samples):
         one = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N, path=path)
         assert torch.equal(r["grid"][i].cpu(), torch.cat([one["voxel"].reshape(1), one["origin"]])), i
         assert torch.equal(r["pass1_hand"][i], one["pass1_hand"].reshape(-1)) and torch.equal(r["pass1_obj"][i], one["pass1_obj"].reshape(-1))
         assert torch.equal(r["hand"][i], one["hand"].reshape(-1)) and torch.equal(r["obj"][i], one["obj"].reshape(-1)), i
     # bounding-box-only pass 1 (what create_mesh_combined_decoder runs) gives the same lattice
-    r2 = batch.two_pass(N, 3, "reference", kind, keep_pass1=False)
+    r2 = batch.two_pass(N, 3, "reference", lvl, keep_pass1=False)
     assert r2["pass1_hand"] is None and torch.equal(r2["grid"], r["grid"]) and torch.equal(r2["hand"], r["hand"])
 
 
@@ -211,7 +217,7 @@ def test_f16_f8_falls_back_when_activations_leave_the_fp8_range():
     N = 24
     before = engine.STATS["f8_rejected"]
     ht, ot, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="f8")
-    assert engine.STATS["f8_rejected"] == before + 1 and "f16x3" in bound.kinds_used
+    assert engine.STATS["f8_rejected"] == before + 1 and bound.last_kind == "f16x3"
     hs, os_, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], path="simt")
     assert (ht - hs).abs().max() <= 1e-5 and (ot - os_).abs().max() <= 1e-5
 
@@ -225,10 +231,13 @@ def test_full_grid_auto_path_within_contract_of_the_fp32_kernel(init, gain, N):
     s = synthetic.make_sample(31).to(DEV)
     bound = engine.get_engine(dec, DEV).bind(s.latent, s.specs, s.mano_results, s.obj_results)
     ht, ot, _, bt = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="auto")
+    kind = bound.last_kind
     hs, os_, _, bs = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path="simt")
     eh, eo = float((ht - hs).abs().max()), float((ot - os_).abs().max())
-    assert eh <= TOL and eo <= TOL, (eh, eo, bound.kinds_used)
-    assert ("f16+2xe4m3" in bound.kinds_used) == (init != "plain"), bound.kinds_used
+    print(f"{init} gain {gain} N={N}: {kind}, max |sdf - fp32 kernel| = {max(eh, eo):.2e}")
+    assert eh <= TOL and eo <= TOL, (eh, eo, kind)
+    assert (kind == "f16+2xe4m3") == (init != "plain"), kind
+    assert max(eh, eo) <= 2.5 * engine.CALIB_TOL        # 16.7 M points vs the 4 k calibration points: the tail stays close
     # the box may differ only where a value sits within the kernels' rounding of zero
     near0 = ((hs.abs() < 2e-5).sum() + (os_.abs() < 2e-5).sum()).item()
     assert torch.equal(bt, bs) or near0 > 0
