@@ -41,6 +41,7 @@ CALIB_TOL = 4e-6
 STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0, "simt_launches": 0}
 FALLBACKS = STATS                # old name
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
+KERNEL_EVENTS = None             # bench.py: a list -> every asdf_tc_eval is bracketed by CUDA events on its stream
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
 
@@ -212,7 +213,13 @@ class BoundSample:
         l.bbox_dev = None if box is None else box.data_ptr()
         l.status_dev = status.data_ptr()
         with torch.cuda.device(dev):
+            if KERNEL_EVENTS is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = _lib.lib().asdf_tc_eval(C.byref(l), C.byref(q), _lib.stream_ptr(dev))
+            if KERNEL_EVENTS is not None:
+                e1.record()
+                KERNEL_EVENTS.append((KIND_NAMES[kind], self.S * n, e0, e1))
         _lib.check(rc, "asdf_tc_eval")
         LAUNCHES["count"] += 1
         STATS["f8_launches" if kind == F16_F8 else "f16_launches"] += 1

@@ -224,7 +224,7 @@ def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
     res = amesh.create_mesh_combined_decoder(hb, ob, label, dec, s.latent, s.mano_results, s.obj_results,
                                              None, s.specs, prefix, N=meta["N"], max_batch=2 ** 18,
                                              label_out=label)
-    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob, cls_branch=label)
     vs = float(vols["voxel"]); org = vols["origin"].tolist()
     for tag, use in (("hand", hb), ("obj", ob)):
         path = f"{prefix}_{tag}.ply"

@@ -199,8 +199,9 @@ def test_batched_launch_is_bit_identical_to_single_sample_launches(path):
 def test_combined_decoder_on_the_tensor_core_kernel(name, path):
     """CombinedDecoder (one MLP, two outputs) through k1_tc: golden fields of the real reference."""
     vols, g, dec = _volumes(name, path)
-    assert vols["bound"].kinds_used <= {"f16x3", "f16+2xe4m3"} and vols["bound"].kinds_used
-    _check_fields(vols, g)
+    worst = _check_fields(vols, g)
+    print(f"combined {name} [{path}]: {vols['bound'].last_kind}, max |sdf - reference| = {worst:.2e}")
+    assert vols["bound"].last_kind in (("f16x3",) if path == "f16" else ("f16x3", "f16+2xe4m3"))
 
 
 def test_f16_f8_falls_back_when_activations_leave_the_fp8_range():
