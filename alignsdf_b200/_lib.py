@@ -97,7 +97,7 @@ def lib():
     L.asdf_mc_count.restype = C.c_int
     L.asdf_mc_count.argtypes = [vp, C.POINTER(McParams), vp, vp, vp]
     L.asdf_mc_emit.restype = C.c_int
-    L.asdf_mc_emit.argtypes = [vp, C.POINTER(McParams), vp, vp, vp, vp, vp, vp]
+    L.asdf_mc_emit.argtypes = [vp, C.POINTER(McParams), vp, C.c_int64, vp, vp, vp, vp, vp]
     L.asdf_cc_label.restype = C.c_int
     L.asdf_cc_label.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
     L.asdf_cc_stats.restype = C.c_int

@@ -547,11 +547,11 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         scratch = torch.empty(L.asdf_mc_scratch_bytes(C.byref(p)), dtype=torch.uint8, device=dev)
-        totals = torch.empty(4, dtype=torch.int64, device=dev)
+        totals = torch.empty(5, dtype=torch.int64, device=dev)
         _lib.check(L.asdf_mc_count(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(totals), st),
                    "asdf_mc_count")
         LAUNCHES["count"] += 5
-        nv, nt, mn, mx = (int(x) for x in totals.cpu())
+        nv, nt, mn, mx, nseg = (int(x) for x in totals.cpu())
         if check_range and not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
             raise ValueError("Surface level must be within volume data range.")
         verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
@@ -559,7 +559,7 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
         faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
         keys = torch.empty(nv, dtype=torch.int64, device=dev) if want_keys else None
         if nv > 0 or nt > 0:
-            _lib.check(L.asdf_mc_emit(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(verts),
+            _lib.check(L.asdf_mc_emit(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), nseg, _lib.ptr(verts),
                                       _lib.ptr(points), _lib.ptr(faces), _lib.ptr(keys), st),
                        "asdf_mc_emit")
             LAUNCHES["count"] += 1

@@ -175,14 +175,15 @@ typedef struct {
   float origin[3];         /* points = origin + verts (utils/mesh.py:360-363) */
 } asdf_mc_params;
 size_t asdf_mc_scratch_bytes(const asdf_mc_params* p);
-/* Pass 1: classify + count + scan.  totals_dev: int64[4] = {n_verts, n_tris, min_bits, max_bits}
- * (field min/max as ordered-int bit patterns, for the "level outside data range" check). */
+/* Pass 1: classify + count + scan (the field is read once).  totals_dev: int64[5] = {n_verts, n_tris, min_bits,
+ * max_bits, n_segments} (field min/max as ordered-int bit patterns, for the "level outside data range" check;
+ * n_segments = runs of 32 grid points that own a vertex or a triangle, handed back to asdf_mc_emit). */
 int asdf_mc_count(const float* vol_dev, const asdf_mc_params* p, void* scratch_dev,
                   int64_t* totals_dev, void* stream);
 /* Pass 2: emit.  verts_dev [V,3] f32 (array-axis order * spacing, what marching_cubes returns),
  * points_dev [V,3] f32 (origin + verts) or NULL, faces_dev [F,3] int32,
  * keys_dev [V] uint64 global vertex keys (for slab stitching) or NULL. */
-int asdf_mc_emit(const float* vol_dev, const asdf_mc_params* p, const void* scratch_dev,
+int asdf_mc_emit(const float* vol_dev, const asdf_mc_params* p, const void* scratch_dev, int64_t n_segments,
                  float* verts_dev, float* points_dev, int32_t* faces_dev, uint64_t* keys_dev,
                  void* stream);
 
