@@ -15,7 +15,7 @@ ASDF_MAX_LAYERS = 8
 ASDF_MAX_POINT_DIM = 64
 QUERY_GRID_REFERENCE, QUERY_GRID_REGULAR, QUERY_POINTS = 0, 1, 2
 TC_F16X3, TC_F16_F8 = 0, 1          # asdf_tc_launch.kind
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalignsdf_b200.so")
 
@@ -54,7 +54,7 @@ class TcBindDesc(C.Structure):
 class McParams(C.Structure):
     _fields_ = [("n0", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32), ("full1", C.c_int32),
                 ("full2", C.c_int32), ("index0_offset", C.c_int64), ("iso", C.c_float),
-                ("spacing", C.c_double * 3), ("origin", C.c_float * 3)]
+                ("spacing", C.c_double * 3), ("origin", C.c_float * 3), ("grid_dev", C.c_void_p)]
 
 
 _lib = None

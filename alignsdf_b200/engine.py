@@ -42,6 +42,7 @@ STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0,
 FALLBACKS = STATS                # old name
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 KERNEL_EVENTS = None             # bench.py: a list -> every asdf_tc_eval is bracketed by CUDA events on its stream
+MC_EVENTS = None                 # bench.py: a list -> (algorithmic bytes, count e0, e1, emit e0, e1) per marching_cubes call
 _GRID_MODES = {"reference": _lib.QUERY_GRID_REFERENCE, "regular": _lib.QUERY_GRID_REGULAR}
 
 
@@ -94,6 +95,7 @@ class BoundSample:
         self.tc_ok = engine.tc_supported and not feature_mode and not self.nerf_freqs
         self._two_outputs = engine.n_outputs == 2
         self._simt = {}                         # sample index -> (pack, sample tensor, desc)
+        self._affines = {}                      # sample index -> embedding_affine
         self._tc_inputs = None
         self._tc_blocks = {}                    # kind -> (blocks, p_absmax, bind status)
         self._calib = None                      # device f32[2]: max |F16_F8 - fp32|, max |F16X3 - fp32| on the calibration points
@@ -111,8 +113,9 @@ class BoundSample:
             return self._simt[i]
         engine, topo, dev = self.engine, self.engine.topo, self.device
         latent, specs, mano, obj = self.inputs[i]
-        branches = packer.fold_decoder(topo, latent, specs, mano, obj, self.feature_mode)
-        pack = packer.pack_simt(branches)
+        branches = packer.fold_decoder(topo, latent, specs, mano, obj, self.feature_mode,
+                                       affine=None if self.feature_mode else self._affine(i))
+        pack = packer.pack_simt(branches, want_static=engine.simt_static is None)
         if engine.simt_static is None:      # static weights do not depend on the sample
             engine.simt_static = torch.from_numpy(pack.static).to(dev)
         sample = torch.from_numpy(pack.sample).to(dev, non_blocking=True)
@@ -152,6 +155,13 @@ class BoundSample:
         self.kinds_used.add("simt")
         return hand, obj, cls, logits
 
+    def _affine(self, i):
+        """(A [pf,3], c [pf]) of sample i's pose-align embedding (float64), computed once."""
+        if i not in self._affines:
+            _, specs, mano, obj = self.inputs[i]
+            self._affines[i] = packer.embedding_affine(specs, mano, obj)
+        return self._affines[i]
+
     # ------------------------------------------------------------------ tensor-core kernel
     def _ensure_tc_inputs(self):
         if self._tc_inputs is None:
@@ -164,7 +174,7 @@ class BoundSample:
             for i, (_, specs, mano, obj) in enumerate(self.inputs):
                 if specs.get("PixelAlign", False):
                     raise AsdfError("PixelAlign samples are evaluated by alignsdf_b200.pixel_align, not folded")
-                A, c = packer.embedding_affine(specs, mano, obj)
+                A, c = self._affine(i)
                 aff[i, :A.shape[0], :3], aff[i, :A.shape[0], 3] = A, c
             self._tc_inputs = (lat.to(dev, non_blocking=True).contiguous(),
                                torch.from_numpy(aff).to(dev, non_blocking=True))
@@ -259,37 +269,48 @@ class BoundSample:
             lvl = self.engine.level
         return lvl if self.tc_ok else LEVEL_SIMT
 
-    def verify(self):
-        """Host check (one small D2H, synchronises) of everything launched since the last call: the calibration
-        errors and the operand-range / bind flags of the tensor-core launches.  -> the lowest level whose results
-        can be trusted for this batch; launches made below it must be repeated at that level."""
+    def pending_flags(self):
+        """Device int32[4] describing everything launched since the last call, without waiting for it:
+        [OR of the status | bind words of the F16_F8 launches, the same for the F16X3 launches, bit pattern of the
+        calibration error of F16_F8, of F16X3 (0 = no calibration result pending)].  Words of several ranks
+        combine with an elementwise MAX (positive floats order like their bit patterns)."""
         pending, self._pending = self._pending, []
-        check_calib = self._calib is not None and not self._calib_checked
+        dev = self.device
+        words = [torch.zeros((), dtype=torch.int32, device=dev) for _ in range(2)]
+        for lvl, st, bst in pending:
+            words[lvl] = words[lvl] | st.reshape(()) | bst.reshape(())
+        if self._calib is not None and not self._calib_checked:
+            cal = self._calib.to(torch.float32).view(torch.int32)
+        else:
+            cal = torch.zeros(2, dtype=torch.int32, device=dev)
+        return torch.cat([torch.stack(words), cal])
+
+    def decide(self, flags):
+        """Host half of the check: ``flags`` = the four ints of pending_flags() (of this process, or the MAX over the
+        ranks of a slab group -- every rank then takes the same decision).  -> the lowest level whose results can
+        be trusted for this batch; launches made below it must be repeated at that level."""
+        w8, w16, b8, b16 = (int(x) for x in flags)
         eng = self.engine
         need = self._level_floor
-        if pending or check_calib:
-            words = [(st | bst).reshape(()).to(torch.float32) for _, st, bst in pending]
-            if check_calib:
-                words += [self._calib[0], self._calib[1]]
-            vals = torch.stack(words).cpu().tolist()
-            if check_calib:
+        if b8 or b16:
+            e8, e16 = (float(np.array([b], np.int32).view(np.float32)[0]) for b in (b8, b16))
+            if not self._calib_checked:
                 self._calib_checked = True
-                e16, e8 = vals.pop(), vals.pop()
                 eng.calib["samples"] += self.S
                 for key, e in (("f8", e8), ("f16", e16)):
                     if np.isfinite(e):
                         eng.calib[key] = max(e, eng.calib.get(key) or 0.0)
                 self.calib_err = (e8, e16)
-                if not e8 <= CALIB_TOL:             # also catches NaN
-                    need = max(need, LEVEL_F16)
-                    if not e16 <= CALIB_TOL:
-                        need = LEVEL_SIMT
-            for (lvl, _, _), v in zip(pending, vals):
-                if int(v) == 0:
-                    continue
-                # F16_F8: an activation beyond the e4m3 range -> all-fp16 kind; F16X3 range flag or a bind
-                # failure (operands do not fit fp16): only the generic kernel is left
-                need = max(need, LEVEL_F16 if (lvl == LEVEL_F8 and not (int(v) & 2)) else LEVEL_SIMT)
+            if not e8 <= CALIB_TOL:             # also catches NaN
+                need = max(need, LEVEL_F16)
+                if not e16 <= CALIB_TOL:
+                    need = LEVEL_SIMT
+        # F16_F8: an activation beyond the e4m3 range -> all-fp16 kind; F16X3 range flag or a bind failure
+        # (operands do not fit fp16): only the generic kernel is left
+        if w8:
+            need = max(need, LEVEL_SIMT if (w8 & 2) else LEVEL_F16)
+        if w16:
+            need = LEVEL_SIMT
         self._level_floor = need
         if need > eng.level:
             if eng.level == LEVEL_F8:
@@ -299,6 +320,14 @@ class BoundSample:
             if eng.path == "auto":
                 eng.level = need                    # sticky per decoder
         return need
+
+    def verify(self):
+        """Host check (one small D2H, synchronises) of everything launched since the last call: the calibration
+        errors and the operand-range / bind flags of the tensor-core launches.  -> the lowest level whose results
+        can be trusted for this batch; launches made below it must be repeated at that level."""
+        if not self._pending and (self._calib is None or self._calib_checked):
+            return self._level_floor
+        return self.decide(self.pending_flags().cpu().tolist())
 
     # ------------------------------------------------------------------ single-sample calls (drop-in API)
     def _run(self, q, n, want_cls, bbox, path, p_absmax=2.0, want_logits=False):
@@ -518,18 +547,11 @@ def get_engine(decoder, device) -> DecoderEngine:
 # ----------------------------------------------------------------------------
 # marching cubes
 # ----------------------------------------------------------------------------
-def _decode_ordered(bits: int) -> float:
-    b = bits if bits >= 0 else bits ^ 0x7FFFFFFF
-    return float(np.array([b], np.int32).view(np.float32)[0])
-
-
-def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
-                   index0_offset=0, want_keys=False, check_range=True):
-    """GPU marching cubes.  vol: CUDA f32 [n0,n1,n2].  Returns dict of CUDA tensors
-    verts [V,3] (array-axis order x spacing), points [V,3] (= origin + verts), faces [F,3] int32,
-    keys [V] int64 (when want_keys).  Raises ValueError like skimage when level is outside the
-    data range (the reference catches it, utils/mesh.py:353-358); ``check_range=False`` (z-slabs,
-    where an empty slab is normal) returns empty tensors instead."""
+def mc_count(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), index0_offset=0,
+             grid_dev=None):
+    """First half of marching cubes (classify + count + scan; the field is read once), asynchronous.
+    ``grid_dev``: CUDA f32[4] = (voxel, origin) overriding spacing / origin (a row of asdf_regrid's output).
+    -> (totals int64[5] on the device: n_verts, n_tris, min bits, max bits, n_segments; handle for mc_emit)"""
     _lib.require_cuda(vol, "vol")
     vol = vol.to(torch.float32).contiguous()
     if vol.dim() != 3:
@@ -542,28 +564,65 @@ def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin
     for k in range(3):
         p.spacing[k] = float(spacing[k])
         p.origin[k] = float(origin[k])
+    p.grid_dev = None if grid_dev is None else grid_dev.data_ptr()
     L = _lib.lib()
     dev = vol.device
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         scratch = torch.empty(L.asdf_mc_scratch_bytes(C.byref(p)), dtype=torch.uint8, device=dev)
         totals = torch.empty(5, dtype=torch.int64, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if MC_EVENTS is not None else None
+        if ev:
+            ev[0].record()
         _lib.check(L.asdf_mc_count(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), _lib.ptr(totals), st),
                    "asdf_mc_count")
-        LAUNCHES["count"] += 5
-        nv, nt, mn, mx, nseg = (int(x) for x in totals.cpu())
-        if check_range and not (_decode_ordered(mn) <= float(np.float32(level)) <= _decode_ordered(mx)):
-            raise ValueError("Surface level must be within volume data range.")
+        if ev:
+            ev[1].record()
+        LAUNCHES["count"] += 4
+    return totals, (vol, p, scratch, grid_dev, ev)
+
+
+def mc_emit(handle, nv, nt, nseg, want_keys=False):
+    """Second half: ``nv, nt, nseg`` = totals[0], totals[1], totals[4] of mc_count read back by the caller.
+    -> dict(verts, points, faces, keys) of CUDA tensors."""
+    vol, p, scratch, _, ev = handle
+    L = _lib.lib()
+    dev = vol.device
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
         verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
         points = torch.empty((nv, 3), dtype=torch.float32, device=dev)
         faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
         keys = torch.empty(nv, dtype=torch.int64, device=dev) if want_keys else None
+        if ev:
+            ev[2].record()
         if nv > 0 or nt > 0:
             _lib.check(L.asdf_mc_emit(_lib.ptr(vol), C.byref(p), _lib.ptr(scratch), nseg, _lib.ptr(verts),
                                       _lib.ptr(points), _lib.ptr(faces), _lib.ptr(keys), st),
                        "asdf_mc_emit")
             LAUNCHES["count"] += 1
+        if ev:
+            ev[3].record()
+            MC_EVENTS.append((4 * vol.numel() + 12 * nv + 12 * nt, *ev))
     return dict(verts=verts, points=points, faces=faces, keys=keys)
+
+
+def marching_cubes(vol: torch.Tensor, level=0.0, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
+                   index0_offset=0, want_keys=False, check_range=True):
+    """GPU marching cubes.  vol: CUDA f32 [n0,n1,n2].  Returns dict of CUDA tensors
+    verts [V,3] (array-axis order x spacing), points [V,3] (= origin + verts), faces [F,3] int32,
+    keys [V] int64 (when want_keys).  Raises ValueError like skimage when level is outside the
+    data range (the reference catches it, utils/mesh.py:353-358); ``check_range=False`` (z-slabs,
+    where an empty slab is normal) returns empty tensors instead."""
+    totals, handle = mc_count(vol, level, spacing, origin, index0_offset)
+    nv, nt, _, _, nseg = (int(x) for x in totals.cpu())
+    if check_range and nv == 0 and nt == 0:
+        # no sign change anywhere: only now does the field's range matter (a surface implies min < level <= max),
+        # so the streaming pass does not carry a min / max reduction
+        mn, mx = (float(x) for x in torch.aminmax(handle[0]))
+        if not (mn <= float(np.float32(level)) <= mx):
+            raise ValueError("Surface level must be within volume data range.")
+    return mc_emit(handle, nv, nt, nseg, want_keys)
 
 
 def ply_face_records(faces: torch.Tensor) -> torch.Tensor:
@@ -575,6 +634,35 @@ def ply_face_records(faces: torch.Tensor) -> torch.Tensor:
         rec[:, 0] = 3
         rec[:, 1:] = faces.contiguous().view(torch.uint8).view(F, 12)
     return rec
+
+
+def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor):
+    """Write the binary PLY of a mesh that lives on the GPU (same bytes as trimesh_lite.export_ply) and hand the
+    mesh back as numpy arrays.  The vertex block and the 13-byte face records (built on the device) land in ONE
+    pinned host buffer behind the header, which goes to the file in a single write; the returned arrays are views
+    of pinned memory (torch's caching host allocator recycles it once the mesh is dropped).
+    -> (vertices [V,3] f32, faces [F,3] int32)"""
+    _lib.require_cuda(points, "points")
+    V, F = int(points.shape[0]), int(faces.shape[0])
+    header = ("ply\nformat binary_little_endian 1.0\n"
+              f"element vertex {V}\nproperty float x\nproperty float y\nproperty float z\n"
+              f"element face {F}\nproperty list uchar int vertex_indices\nend_header\n").encode("ascii")
+    pad = (-len(header)) % 16
+    off = pad + len(header)
+    host = torch.empty(off + 12 * V + 13 * F, dtype=torch.uint8, pin_memory=True)
+    host_faces = torch.empty((F, 3), dtype=torch.int32, pin_memory=True)
+    dev = points.device
+    with torch.cuda.device(dev):
+        rec = ply_face_records(faces)
+        host[off:off + 12 * V].copy_(points.to(torch.float32).contiguous().view(torch.uint8).reshape(-1), non_blocking=True)
+        host[off + 12 * V:].copy_(rec.reshape(-1), non_blocking=True)
+        host_faces.copy_(faces.contiguous(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    buf = host.numpy()
+    buf[pad:off] = np.frombuffer(header, dtype=np.uint8)
+    with open(path, "wb") as fh:
+        fh.write(buf[pad:])
+    return host[off:off + 12 * V].view(torch.float32).view(V, 3).numpy(), host_faces.numpy()
 
 
 def select_component(points: torch.Tensor, faces: torch.Tensor, verts_local: torch.Tensor, dims, spacing):

@@ -108,21 +108,28 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
     # trimesh.graph.split + "largest area piece if more than one" (:371-381) on the GPU (csrc/cc.cu); only the
     # kept component and the raw marching-cubes arrays the reference returns travel to the host
     sel_points, sel_faces, _ = _engine.select_component(out["points"], out["faces"], out["verts"], vol.shape, [vs] * 3)
-    ply_faces = _engine.ply_face_records(sel_faces).cpu().numpy()
-    mesh_points = sel_points.cpu().numpy()                 # origin + verts (f32), :360-363
     whole = sel_faces is out["faces"]
-    sel_faces_np = sel_faces.cpu().numpy()
+    # x * 1 + 0 (what the reference applies to the object mesh outside eval_mode, utils/mesh.py:186-194) is the identity
+    identity = ((scale is None or bool(np.all(np.asarray(scale) == 1)))
+                and (offset is None or not bool(np.any(np.asarray(offset)))))
+    if identity:
+        # vertex block + face records -> one pinned buffer -> one write; origin + verts (f32), :360-363
+        mesh_points, sel_faces_np = _engine.export_ply_from_device(ply_filename_out, sel_points, sel_faces)
+    else:
+        ply_faces = _engine.ply_face_records(sel_faces).cpu().numpy()
+        mesh_points = sel_points.cpu().numpy()
+        sel_faces_np = sel_faces.cpu().numpy()
+        if scale is not None:
+            mesh_points = mesh_points * scale
+        if offset is not None:
+            mesh_points = mesh_points + offset
+        export_ply_records(ply_filename_out, mesh_points, ply_faces)
     if raw_on_device:
         verts, faces = out["verts"], out["faces"]
     else:
         verts = out["verts"].cpu().numpy()
         faces = sel_faces_np if whole else out["faces"].cpu().numpy()
-    if scale is not None:
-        mesh_points = mesh_points * scale
-    if offset is not None:
-        mesh_points = mesh_points + offset
     source_mesh = Mesh(mesh_points, sel_faces_np)
-    export_ply_records(ply_filename_out, mesh_points, ply_faces)
     res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
     return res + (source_mesh,) if return_mesh else res
 

@@ -215,8 +215,9 @@ class FoldedBranch:
 
 
 def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
-                 feature_mode: bool = False):
-    """Fold latent (+ embedding affine unless ``feature_mode``) into the layers."""
+                 feature_mode: bool = False, affine=None):
+    """Fold latent (+ embedding affine unless ``feature_mode``) into the layers.  ``affine``: the result of
+    ``embedding_affine`` for this sample when the caller already has it."""
     z = latent.detach().cpu().double().numpy().reshape(-1)
     L = topo.latent_size
     if z.shape[0] != L:
@@ -228,7 +229,7 @@ def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
         A_full = np.eye(topo.point_feat_size)
         c_full = np.zeros(topo.point_feat_size)
     else:
-        A_full, c_full = embedding_affine(specs, mano_results, obj_results)
+        A_full, c_full = affine if affine is not None else embedding_affine(specs, mano_results, obj_results)
     out = []
     for tag, prefix in topo.branches:
         idx = branch_feature_index(topo, tag)
@@ -326,7 +327,9 @@ class SimtPack:
     max_width: int
 
 
-def pack_simt(branches) -> SimtPack:
+def pack_simt(branches, want_static=True) -> SimtPack:
+    """``want_static=False``: only the per-sample part and the table (the weight block does not depend on the
+    sample and is uploaded once per decoder)."""
     n_layers = len(branches[0].layers)
     static, sample, table = [], [], []
     off_s = off_p = 0
@@ -340,7 +343,7 @@ def pack_simt(branches) -> SimtPack:
             npad = _pad8(n)
             h = 0 if fl.Wx is None else fl.Wx.shape[1]
             max_w = max(max_w, npad, h)
-            if h:
+            if h and want_static:
                 wt = np.zeros((h, npad), np.float32)
                 wt[:, :n] = fl.Wx.T
                 static.append(wt.reshape(-1))
@@ -353,11 +356,13 @@ def pack_simt(branches) -> SimtPack:
             off_w = off_s
             off_s += h * npad
             if fl.ln is not None:
-                static.append(np.concatenate([fl.ln[0], fl.ln[1]]).astype(np.float32))
+                if want_static:
+                    static.append(np.concatenate([fl.ln[0], fl.ln[1]]).astype(np.float32))
                 off_ln = off_s
                 off_s += 2 * n
                 if off_s % 4:                           # keep the next weight block 16-byte aligned
-                    static.append(np.zeros(4 - off_s % 4, np.float32))
+                    if want_static:
+                        static.append(np.zeros(4 - off_s % 4, np.float32))
                     off_s += 4 - off_s % 4
             table.append((h, n, npad, int(fl.M is not None), off_w, off_p, off_ln, 0))
             off_p += npad * (D + 1)

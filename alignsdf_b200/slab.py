@@ -4,18 +4,22 @@ The reference only has sample-level parallelism (dist_reconstruct.py:63-84: one 
 GPU, no communication).  This module adds the north star's second mode: grid axis 0 is cut into
 ``world`` contiguous slabs, one process per GPU (torchrun / torch.distributed):
 
-  pass 1   each rank evaluates its slab and reduces a local bbox   -> ONE all_reduce(MIN) of 12 ints
-  re-grid  identical arithmetic on every rank                       (utils/mesh.py:249-254)
+  pass 1   each rank evaluates its slab and reduces a local bbox   -> ONE all_reduce(MIN) of 16 ints
+                                                                      (bbox + the kernel's range / calibration flags)
+  re-grid  identical arithmetic on every rank, on the device        (utils/mesh.py:249-254, asdf_regrid)
   pass 2   each rank evaluates its slab of the refit grid
-  halo     every rank publishes its first plane (both fields)       -> ONE all_gather of [2,N,N] f32
-  MC       each rank meshes [z0, z1] (its slab + the neighbour's first plane) with global keys
-  gather   vertex / face / key lists go to rank 0                   -> all_gather of counts + ONE packed gather
-  stitch   rank 0 merges duplicate boundary vertices by key; the result is bit-identical to the
-           single-GPU mesh (same vertex order = key order, same face order = cell order).
+  halo     every rank sends its first plane (both fields) to the rank below it    -> ONE neighbour send / recv
+  MC       each rank counts the surface of [z0, z1] (its slab + the neighbour's first plane)
+  sizes    vertex / face counts and the pass-2 flags of every rank -> ONE all_gather of 8 ints, read on the host:
+           the only point where a rank waits for its GPU.  If any rank's flags reject the kernel kind in use,
+           EVERY rank repeats the sample with the next safer kind (the stitched field never mixes two kinds).
+  gather   vertices / faces / global keys go to rank 0 un-padded   -> point-to-point sends of the exact sizes
+  stitch   rank 0 drops each slab's copies of the next slab's first-plane vertices and re-indexes their faces
+           by key look-up; the result is bit-identical to the single-GPU mesh (same vertex order = key order,
+           same face order = cell order).
 
 The numerical kernels are injected (``Backend``) so the collective / stitching logic can be tested
-on CPU with gloo (tests/test_slab_gloo.py uses the oracle as backend); ``GpuBackend`` is the
-product backend.
+on CPU with gloo (tests/test_slab_gloo.py uses the oracle as backend); ``gpu_backend`` is the product one.
 """
 from __future__ import annotations
 
@@ -26,6 +30,8 @@ import torch
 import torch.distributed as dist
 
 INT_MAX = 2 ** 31 - 1
+INT64_MAX = 2 ** 63 - 1
+N_FLAGS = 4                    # engine.BoundSample.pending_flags()
 
 
 def slab_planes(N: int, rank: int, world: int, relief: int = 0):
@@ -46,155 +52,218 @@ def slab_planes(N: int, rank: int, world: int, relief: int = 0):
 
 
 def default_relief(N: int, world: int) -> int:
-    """Planes to take off rank 0 (see slab_planes): the gather + stitch tail is worth ~3.4 planes of two
-    passes at any N (both scale with N^2), shared with the other ranks -> 3.4 (world-1)/world, if slabs are thick
+    """Planes to take off rank 0 (see slab_planes): the gather + stitch tail is worth ~2 planes of two
+    passes at any N (both scale with N^2), shared with the other ranks -> 2 (world-1)/world, if slabs are thick
     enough for it not to matter otherwise."""
     if world < 2 or N // world < 16:
         return 0
-    return int(round(3.4 * (world - 1) / world))
+    return int(round(RELIEF_PLANES * (world - 1) / world))
+
+
+RELIEF_PLANES = 2.0
 
 
 @dataclass
 class Backend:
-    """eval(begin, end, voxel, origin, bbox_mask) -> (hand [n], obj [n], box int32[12] | None);
-    mc(vol [m,N,N], voxel, origin, index0_offset) -> (verts [V,3] f32, points [V,3] f32, faces [F,3] i32, keys [V] i64)"""
-    eval: callable
-    mc: callable
+    """The numerical kernels behind the slab logic.  All calls are asynchronous where the device allows it.
+
+    pass1(begin, end, mask)          -> (box int32[12], flags int32[N_FLAGS])      bbox-only evaluation of grid indices [begin, end)
+    regrid(box, mask)                -> grid f32[4] = (voxel, origin x3)           utils/mesh.py:198-256 on the reduced box
+    pass2(begin, end, grid)          -> (hand [n], obj [n], flags int32[N_FLAGS])
+    mc_count(vol, grid, z0)          -> (totals int64[5]: n_verts, n_tris, -, -, n_segments; handle)
+    mc_emit(handle, nv, nt, nseg)    -> (verts [V,3] f32, faces [F,3] i32, keys [V] i64)
+    decide(flags: list[int])         -> True when the sample must be repeated (the backend has switched to a safer
+                                        kernel kind); None: never"""
+    pass1: callable
+    regrid: callable
+    pass2: callable
+    mc_count: callable
+    mc_emit: callable
     device: torch.device
     relief: int = 0            # planes taken off rank 0 (slab_planes)
+    decide: callable = None
 
 
-def reduce_bbox(box: torch.Tensor, group=None) -> torch.Tensor:
-    """Global bbox from per-rank {min x3, max x3} x2 with a single MIN all-reduce (max is negated)."""
-    b = box.clone().to(torch.int32)
-    sign = torch.tensor([1, 1, 1, -1, -1, -1] * 2, dtype=torch.int32, device=b.device)
-    b = b * sign
-    dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
-    return b * sign
+def _peer(group, r):
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def reduce_bbox(box: torch.Tensor, flags: torch.Tensor = None, group=None):
+    """Global bbox from per-rank {min x3, max x3} x2, and the elementwise MAX of the flag words, with a single MIN
+    all-reduce (maxima travel negated).  -> (box int32[12], flags int32[N_FLAGS])"""
+    b = box.reshape(-1).to(torch.int32)
+    if flags is None:
+        flags = torch.zeros(N_FLAGS, dtype=torch.int32, device=b.device)
+    sign = torch.tensor([1, 1, 1, -1, -1, -1] * 2 + [-1] * N_FLAGS, dtype=torch.int32, device=b.device)
+    packed = torch.cat([b, flags.to(torch.int32)]) * sign
+    dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
+    packed = packed * sign
+    return packed[:12], packed[12:]
 
 
 def exchange_halo(first_planes: torch.Tensor, rank: int, world: int, group=None):
-    """all_gather of every rank's first plane; returns the next rank's plane (None on the last)."""
-    buf = [torch.empty_like(first_planes) for _ in range(world)]
-    dist.all_gather(buf, first_planes.contiguous(), group=group)
-    return buf[rank + 1] if rank + 1 < world else None
+    """Send this rank's first planes to the rank below, receive the next rank's (None on the last rank):
+    neighbour-only point-to-point transfers."""
+    ops, recv = [], None
+    send = first_planes.contiguous()
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, send, _peer(group, rank - 1), group))
+    if rank + 1 < world:
+        recv = torch.empty_like(send)
+        ops.append(dist.P2POp(dist.irecv, recv, _peer(group, rank + 1), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
 
 
-def gather_pieces(pieces, rank: int, world: int, group=None):
-    """Gather every rank's mesh pieces on rank 0 with two collectives.
+def _piece_bytes(nv, nf):
+    return (nv * (8 + 12) + nf * 12 + 7) // 8 * 8
 
-    pieces: list (one per surface) of (verts [V,3] f32, faces [F,3] i32, keys [V] i64) on this rank.
-    Returns, on rank 0, a list over ranks of such lists; None elsewhere.  One all_gather of the
-    counts, then one gather of a single packed byte buffer (padded to the largest rank)."""
+
+def gather_pieces(pieces, counts, rank: int, world: int, group=None):
+    """Bring every rank's mesh pieces to rank 0, un-padded.
+
+    pieces: list (one per surface) of (verts [V,3] f32, faces [F,3] i32, keys [V] i64) on this rank;
+    counts: host int array [world, n_surfaces, 2] = (V, F) of every rank (already exchanged).
+    Returns, on rank 0, a list over ranks of such lists; None elsewhere."""
     dev = pieces[0][0].device
-    counts = torch.tensor([[p[0].shape[0], p[1].shape[0]] for p in pieces], dtype=torch.int64, device=dev)
-    allc = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(allc, counts, group=group)
-    allc = torch.stack(allc).cpu()                              # [world, n_surfaces, 2]
-    nbytes = ((allc[:, :, 0] * (12 + 8) + allc[:, :, 1] * 12 + 7) // 8 * 8).sum(1)   # 8-byte aligned blocks
-    cap = max(int(nbytes.max()), 16)
-    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
-    def as_bytes(t):
-        flat_t = torch.empty(t.numel(), dtype=t.dtype, device=t.device)     # fresh unit-stride storage
-        flat_t.copy_(t.reshape(-1))
-        return flat_t.view(torch.uint8)
-    off = 0
-    for p in pieces:                                                         # keys first (8-byte aligned)
-        for t in (p[2], p[0], p[1]):
-            b = as_bytes(t)
-            buf[off:off + b.numel()] = b
-            off += b.numel()
-        off = (off + 7) // 8 * 8
-    recv = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-    dist.gather(buf, recv, dst=0, group=group)
-    if rank != 0:
-        return None
-    out = []
-    for r in range(world):
+    nbytes = [sum(_piece_bytes(int(counts[r, s_i, 0]), int(counts[r, s_i, 1])) for s_i in range(len(pieces)))
+              for r in range(world)]
+
+    def pack():
+        buf = torch.empty(max(nbytes[rank], 8), dtype=torch.uint8, device=dev)
+        off = 0
+        for v, f, k in pieces:                                               # keys first (8-byte aligned)
+            for t in (k, v, f):
+                n = t.numel() * t.element_size()
+                if n:
+                    buf[off:off + n].view(t.dtype).copy_(t.reshape(-1))
+                off += n
+            off = (off + 7) // 8 * 8
+        return buf
+
+    def unpack(buf, r):
         off, lst = 0, []
         for s_i in range(len(pieces)):
-            nv, nf = int(allc[r, s_i, 0]), int(allc[r, s_i, 1])
-            k = recv[r][off:off + nv * 8].view(torch.int64); off += nv * 8
-            v = recv[r][off:off + nv * 12].view(torch.float32).view(nv, 3); off += nv * 12
-            f = recv[r][off:off + nf * 12].view(torch.int32).view(nf, 3); off += nf * 12
+            nv, nf = int(counts[r, s_i, 0]), int(counts[r, s_i, 1])
+            k = buf[off:off + nv * 8].view(torch.int64); off += nv * 8
+            v = buf[off:off + nv * 12].view(torch.float32).view(nv, 3); off += nv * 12
+            f = buf[off:off + nf * 12].view(torch.int32).view(nf, 3); off += nf * 12
             off = (off + 7) // 8 * 8
             lst.append((v, f, k))
-        out.append(lst)
+        return lst
+
+    if rank != 0:
+        if nbytes[rank]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, pack(), _peer(group, 0), group)]):
+                w.wait()
+        return None
+    recv = {r: torch.empty(nbytes[r], dtype=torch.uint8, device=dev) for r in range(1, world) if nbytes[r]}
+    ops = [dist.P2POp(dist.irecv, recv[r], _peer(group, r), group) for r in recv]
+    works = dist.batch_isend_irecv(ops) if ops else []
+    out = [list(pieces)]
+    for w in works:
+        w.wait()
+    empty = torch.empty(8, dtype=torch.uint8, device=dev)
+    for r in range(1, world):
+        out.append(unpack(recv.get(r, empty), r))
     return out
 
 
-def stitch(parts):
-    """parts: per rank (verts, faces, keys) tensors of ONE surface (any device).  Merge duplicate
-    boundary vertices by key; vertex order = key order, face order = rank (== cell) order.
+def stitch(parts, bounds):
+    """parts: per rank (verts, faces, keys) tensors of ONE surface (any device), keys ascending within a rank;
+    bounds: per rank the first key of the NEXT rank's slab (its vertices at or beyond that key are this rank's copies
+    of vertices the next rank owns; INT64_MAX on the last rank).  Drops the copies, re-indexes the faces that use
+    them by key look-up.  Vertex order = key order, face order = rank (== cell) order.
     Returns (verts [V,3] f32, faces [F,3] i32)."""
-    keys = torch.cat([p[2] for p in parts])
-    if keys.numel() == 0:
-        dev = keys.device
+    dev = parts[0][0].device
+    nv = [int(p[2].shape[0]) for p in parts]
+    if sum(nv) == 0:
         return torch.zeros((0, 3), dtype=torch.float32, device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev)
+    keys = torch.cat([p[2] for p in parts])
     verts = torch.cat([p[0] for p in parts])
-    uk, inv = torch.unique(keys, sorted=True, return_inverse=True)
-    # any representative of a duplicated key will do: duplicates are bit-identical by construction
-    first = torch.empty(uk.numel(), dtype=torch.int64, device=keys.device)
-    first[inv] = torch.arange(keys.numel(), device=keys.device)
+    bound = torch.cat([torch.full((n,), int(b), dtype=torch.int64, device=dev) for n, b in zip(nv, bounds)])
+    own = keys < bound
+    own_idx = torch.nonzero(own).flatten()
+    own_keys = keys[own_idx]                                    # ascending: slabs are ordered, each is sorted
+    remap = torch.searchsorted(own_keys, keys)                  # owned: its own rank; copy: the owner's position
     faces, off = [], 0
-    for p in parts:
-        faces.append(inv[p[1].long() + off])
-        off += p[2].shape[0]
-    return verts[first], torch.cat(faces).to(torch.int32)
+    for p, n in zip(parts, nv):
+        faces.append(remap[p[1].long() + off])
+        off += n
+    return verts[own_idx], torch.cat(faces).to(torch.int32)
 
 
-def two_pass_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=True, obj_branch=True,
-                  group=None):
-    """Both evaluation passes on this rank's slab.  Returns dict(hand, obj [nz,N,N], voxel, origin,
-    z0, z1) -- ``voxel``/``origin`` identical on every rank."""
-    from .mesh import _bbox_to_minmax, _regrid
-    z0, z1 = slab_planes(N, rank, world, backend.relief)
-    mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
-    vs1 = 2.0 / (N - 1)
-    _, _, box = backend.eval(z0 * N * N, z1 * N * N, vs1, [-1.0, -1.0, -1.0], mask)
-    if box is None:                                   # empty slab (more ranks than planes)
-        box = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3, dtype=torch.int32,
-                           device=backend.device)
-    box = reduce_bbox(box, group)
-    mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
-    voxel, origin = _regrid(mn, mx, N, vs1)
-    h, o, _ = backend.eval(z0 * N * N, z1 * N * N, float(voxel), origin.tolist(), 0)
-    return dict(hand=h.view(z1 - z0, N, N), obj=o.view(z1 - z0, N, N), voxel=voxel, origin=origin, z0=z0, z1=z1)
+def _grid_host(grid):
+    g = grid.detach().cpu()
+    return g[0].clone(), g[1:4].clone()
 
 
-def mesh_slab(backend: Backend, fields: dict, N: int, rank: int, world: int, which=("hand", "obj"), group=None):
-    """Halo exchange + marching cubes + gather + stitch.  Returns {tag: (verts, points, faces)} as
-    tensors on rank 0's device (None elsewhere); points = f32(origin) + verts like utils/mesh.py:360-363."""
-    z0, z1 = fields["z0"], fields["z1"]
-    nz = z1 - z0
+def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=True, obj_branch=True,
+                     which=("hand", "obj"), group=None, keep_fields=False):
+    """Both evaluation passes on this rank's slab, halo exchange, marching cubes, gather and stitch.
+    Returns dict(grid f32[4] device tensor (voxel, origin; identical on every rank), z0, z1,
+    meshes = {tag: (verts, points, faces)} on rank 0 (None elsewhere), and with ``keep_fields`` hand / obj
+    [nz,N,N])."""
     dev = backend.device
-    first = torch.stack([fields["hand"][0] if nz else torch.zeros(N, N, device=dev),
-                         fields["obj"][0] if nz else torch.zeros(N, N, device=dev)])
-    halo = exchange_halo(first, rank, world, group)
-    vs = float(fields["voxel"])
-    org = fields["origin"].tolist()
-    pieces, tags = [], []
-    for ti, tag in enumerate(("hand", "obj")):
-        if tag not in which:
-            continue
-        vol = fields[tag]
-        if halo is not None and nz:
-            vol = torch.cat([vol, halo[ti:ti + 1]], 0)
-        if vol.shape[0] >= 2:
-            v, _, f, k = backend.mc(vol.contiguous(), vs, org, z0)
+    z0, z1 = slab_planes(N, rank, world, backend.relief)
+    nz = z1 - z0
+    mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
+    plane = N * N
+    while True:
+        box, fl1 = backend.pass1(z0 * plane, z1 * plane, mask)
+        box, fl1 = reduce_bbox(box, fl1, group)
+        grid = backend.regrid(box, mask)
+        h, o, fl2 = backend.pass2(z0 * plane, z1 * plane, grid)
+        fields = dict(hand=h.view(nz, N, N), obj=o.view(nz, N, N))
+        first = torch.stack([fields["hand"][0] if nz else torch.zeros(N, N, device=dev),
+                             fields["obj"][0] if nz else torch.zeros(N, N, device=dev)])
+        halo = exchange_halo(first, rank, world, group)
+        handles, msg = [], []
+        tags = [t for t in ("hand", "obj") if t in which]
+        for tag in tags:
+            vol = fields[tag]
+            if halo is not None and nz:
+                vol = torch.cat([vol, halo[0 if tag == "hand" else 1][None]], 0)
+            if vol.shape[0] >= 2:
+                totals, hd = backend.mc_count(vol.contiguous(), grid, z0)
+                msg.append(totals.to(torch.int64)[[0, 1, 4]])
+            else:
+                hd = None
+                msg.append(torch.zeros(3, dtype=torch.int64, device=dev))
+            handles.append(hd)
+        msg.append(torch.maximum(fl1, fl2.to(fl1.device)).to(torch.int64))
+        msg = torch.cat(msg)
+        allm = [torch.empty_like(msg) for _ in range(world)]
+        dist.all_gather(allm, msg, group=group)
+        allm = torch.stack(allm).cpu().numpy()                 # the one host synchronisation of the sample
+        flags = allm[:, 3 * len(tags):].max(0).tolist()
+        if backend.decide is not None and backend.decide(flags):
+            continue                                           # every rank saw the same flags: all repeat
+        break
+    counts = allm[:, :3 * len(tags)].reshape(world, len(tags), 3)
+    pieces = []
+    for s_i, hd in enumerate(handles):
+        nv, nt, nseg = (int(x) for x in counts[rank, s_i])
+        if hd is not None and (nv or nt):
+            pieces.append(backend.mc_emit(hd, nv, nt, nseg))
         else:
-            v = torch.zeros((0, 3), dtype=torch.float32, device=dev)
-            f = torch.zeros((0, 3), dtype=torch.int32, device=dev)
-            k = torch.zeros((0,), dtype=torch.int64, device=dev)
-        pieces.append((v, f, k)); tags.append(tag)
-    gathered = gather_pieces(pieces, rank, world, group)
-    if rank != 0:
-        return None
-    out = {}
-    org32 = torch.tensor(org, dtype=torch.float32, device=dev)
-    for s_i, tag in enumerate(tags):
-        verts, faces = stitch([gathered[r][s_i] for r in range(world)])
-        out[tag] = (verts, org32[None] + verts, faces)
+            pieces.append((torch.zeros((0, 3), dtype=torch.float32, device=dev),
+                           torch.zeros((0, 3), dtype=torch.int32, device=dev),
+                           torch.zeros((0,), dtype=torch.int64, device=dev)))
+    gathered = gather_pieces(pieces, counts[:, :, :2], rank, world, group)
+    out = dict(grid=grid, z0=z0, z1=z1, meshes=None)
+    if keep_fields:
+        out.update(fields)
+    if rank == 0:
+        bounds = [slab_planes(N, r, world, backend.relief)[1] * plane * 4 if r + 1 < world else INT64_MAX
+                  for r in range(world)]
+        meshes = {}
+        for s_i, tag in enumerate(tags):
+            verts, faces = stitch([gathered[r][s_i] for r in range(world)], bounds)
+            meshes[tag] = (verts, grid[1:4].to(verts.device)[None] + verts, faces)
+        out["meshes"] = meshes
     return out
 
 
@@ -202,22 +271,70 @@ def mesh_slab(backend: Backend, fields: dict, N: int, rank: int, world: int, whi
 # product backend + public entry point
 # ----------------------------------------------------------------------------
 def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
-    from . import engine
+    """Kernels of libalignsdf_b200.so on ``bound`` (an engine.BoundSample of ONE sample).  Nothing here waits for
+    the GPU; the kernel kind is the decoder's current level, checked through the flags (``decide``)."""
+    import ctypes as C
 
-    def ev(begin, end, voxel, origin, bbox_mask):
+    from . import _lib, engine
+    dev = bound.device
+    mode = engine._GRID_MODES[grid_mode]
+    vs1 = 2.0 / (N - 1)
+    state = dict(level=None)
+
+    def zero_flags():
+        return torch.zeros(N_FLAGS, dtype=torch.int32, device=dev)
+
+    def pass1(begin, end, mask):
+        state["level"] = lvl = bound.auto_level(path)
+        box = engine.new_bbox(dev)
         if end <= begin:
-            e = torch.zeros(0, dtype=torch.float32, device=bound.device)
-            return e, e.clone(), None
-        h, o, _, box = bound.eval_grid(N, voxel, origin, grid_mode, begin, end, bbox_mask, path=path)
-        return h, o, box
+            return box[0], zero_flags()
+        q = engine.make_query(mode, N, begin, end, vs1, (-1.0, -1.0, -1.0), bbox_mask=mask)
+        if lvl >= engine.LEVEL_SIMT:
+            bound._launch_simt(q, end - begin, False, box[0])
+        else:
+            bound.launch_tc(engine.LEVEL_KIND[lvl], q, end - begin, False, box)
+        return box[0], bound.pending_flags()
 
-    def mc(vol, voxel, origin, index0_offset):
-        r = engine.marching_cubes(vol, 0.0, [voxel] * 3, origin, index0_offset, want_keys=True,
-                                  check_range=False)
-        return r["verts"], r["points"], r["faces"], r["keys"]
+    def regrid(box, mask):
+        grid = torch.empty((1, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().asdf_regrid(_lib.ptr(box.contiguous()), 1, int(mask), N, float(np.float32(vs1)),
+                                              _lib.ptr(grid), None, _lib.stream_ptr(dev)), "asdf_regrid")
+        engine.LAUNCHES["count"] += 1
+        return grid[0]
+
+    def pass2(begin, end, grid):
+        lvl = state["level"]
+        n = end - begin
+        if n <= 0:
+            e = torch.zeros(0, dtype=torch.float32, device=dev)
+            return e, e.clone(), zero_flags()
+        if lvl >= engine.LEVEL_SIMT:
+            g = grid.cpu().tolist()                            # the generic kernel takes its lattice by value
+            q = engine.make_query(mode, N, begin, end, g[0], g[1:4])
+            h, o, _, _ = bound._launch_simt(q, n, False, None)
+            return h, o, bound.pending_flags()
+        q = engine.make_query(mode, N, begin, end, 0.0, (0.0, 0.0, 0.0))
+        pmax = 2.0                                             # the refit cube lies inside [-1 - 2 voxels, 1 + 2 voxels]
+        h, o, _ = bound.launch_tc(engine.LEVEL_KIND[lvl], q, n, True, None, grid.view(1, 4), pmax)
+        return h[0], o[0], bound.pending_flags()
+
+    def mc_count(vol, grid, z0):
+        return engine.mc_count(vol, 0.0, index0_offset=z0, grid_dev=grid)
+
+    def mc_emit(handle, nv, nt, nseg):
+        r = engine.mc_emit(handle, nv, nt, nseg, want_keys=True)
+        return r["verts"], r["faces"], r["keys"]
+
+    forced = engine._PATH_ALIASES.get(path, path) in engine._PATH_LEVEL or bound.engine.path != "auto"
+
+    def decide(flags):
+        need = bound.decide(flags)
+        return need > state["level"] and not forced           # a forced kind cannot be replaced: keep its results
 
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    return Backend(ev, mc, bound.device, default_relief(N, world))
+    return Backend(pass1, regrid, pass2, mc_count, mc_emit, dev, default_relief(N, world), decide)
 
 
 def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,
@@ -227,38 +344,33 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     initialised process group; rank 0 writes the files and returns the meshes)."""
     import logging
     from . import engine
-    from .trimesh_lite import largest_watertight_component_mc
+    from .trimesh_lite import Mesh, largest_watertight_component_mc
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = engine._device_of(latent_vec)
     bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
     be = gpu_backend(bound, N, grid_mode)
-    fields = two_pass_slab(be, N, rank, world, hand_branch, obj_branch, group)
     which = tuple(t for t, use in (("hand", hand_branch), ("obj", obj_branch)) if use)
-    meshes = mesh_slab(be, fields, N, rank, world, which, group)
+    res = reconstruct_slab(be, N, rank, world, hand_branch, obj_branch, which, group)
     if rank != 0:
         return None
     result = {"hand": None, "obj": None}
-    from .trimesh_lite import Mesh, export_ply_records
-    vs = float(fields["voxel"])
+    vs = float(res["grid"][0])
     for tag in which:
-        verts_d, points_d, faces_d = meshes[tag]
+        verts_d, points_d, faces_d = res["meshes"][tag]
         if faces_d.shape[0] == 0:
             logging.warning("Cannot reconstruct mesh from '{}'".format(f"{filename}_{tag}.ply"))
             continue
         if points_d.is_cuda:
-            # component filter + PLY face records on the GPU (csrc/cc.cu), like mesh.convert_sdf_samples_to_ply
+            # component filter + PLY image on the GPU (csrc/cc.cu), like mesh.convert_sdf_samples_to_ply; the object
+            # mesh's "* scale + offset" with the hand's values (utils/mesh.py:366-369) is x * 1 + 0 outside eval_mode
             sel_p, sel_f, _ = engine.select_component(points_d, faces_d, verts_d, (N, N, N), [vs] * 3)
-            rec = engine.ply_face_records(sel_f).cpu().numpy()
-            points = sel_p.cpu().numpy()
-            if tag == "obj" and hand_branch:
-                points = points * np.array([1]) + np.array([0, 0, 0])  # utils/mesh.py:366-369, hand's values
-            m = Mesh(points, sel_f.cpu().numpy())
             if write:
-                export_ply_records(f"{filename}_{tag}.ply", points, rec)
+                points, faces = engine.export_ply_from_device(f"{filename}_{tag}.ply", sel_p, sel_f)
+            else:
+                points, faces = sel_p.cpu().numpy(), sel_f.cpu().numpy()
+            m = Mesh(points, faces)
         else:                                   # host tensors (gloo tests with the oracle as backend)
-            verts, points, faces = (x.cpu().numpy() for x in meshes[tag])
-            if tag == "obj" and hand_branch:
-                points = points * np.array([1]) + np.array([0, 0, 0])
+            verts, points, faces = (x.cpu().numpy() for x in res["meshes"][tag])
             m = largest_watertight_component_mc(points, faces, verts, (N, N, N), [vs] * 3)
             if write:
                 m.export(f"{filename}_{tag}.ply")

@@ -99,6 +99,21 @@ def make_sample(seed: int, latent_size=256, point_feat_size=9, encode_style="bot
     return Sample(latent, mano_out, obj_out, specs)
 
 
+def make_batch(n: int, base_seed: int = 0, latent_jitter: float = 0.02, **kw):
+    """n samples for ONE decoder whose level sets all exist: independent poses, latents within
+    ``latent_jitter`` (std per entry) of the base sample's.  Independent latents would not do for the
+    non-engineered decoders: their output offset depends far more on the latent than on the query point, so
+    the last-layer bias shift fitted for the base sample leaves most other samples without a zero crossing."""
+    base = make_sample(base_seed, **kw)
+    out = [base]
+    for i in range(1, n):
+        s = make_sample(base_seed + i, **kw)
+        g = _gen(5_000_011 * (base_seed + i + 1))
+        s.latent = (base.latent.double() + latent_jitter * _gauss(g, *base.latent.shape)).float()
+        out.append(s)
+    return out
+
+
 def _fill_linear(g, mod, hidden_gain):
     """Overwrite one (WN)Linear with reproducible values (variance preserving)."""
     out_f, in_f = (mod.weight_v.shape if hasattr(mod, "weight_v") else mod.weight.shape)

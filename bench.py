@@ -17,6 +17,9 @@ object field.  One step therefore answers 2*N^3 hand+object SDF queries.
           bbox, one all_gather of the boundary planes, gather of the mesh pieces to rank 0.
   --impl reference   the reference's own torch-CPU path (oracle port: /root/reference cannot travel
           to the GPU box) on all host cores, on a bounded sample of the same workload.
+  --samples S        number of distinct synthetic samples cycled through (16 = config #3, 1024 = config #4).
+  N > 1 additionally reports ``sample_parallel``: the reference's own multi-GPU mode (dist_reconstruct.py:63-84,
+          independent samples per rank, no communication) through the pipelined batch API, end to end.
 """
 from __future__ import annotations
 
@@ -36,15 +39,20 @@ sys.path.insert(0, ROOT)
 
 F_MIN = 2_086_912          # algorithmic FLOP per hand+obj query after folding
 F_REF = 3_147_776          # FLOP per query as the reference executes it
-N_SAMPLES = 16             # BASELINE config #3: batch of 16 synthetic latents / poses
+N_SAMPLES = 16             # BASELINE config #3: batch of 16 synthetic latents / poses (--samples 1024: config #4)
+DECODER_INIT = "default"   # default-initialised SeparateDecoder, last-layer biases shifted (no wiring)
+DECODER_DESC = "SeparateDecoder 5x512, both/9, torch default init + last-layer bias shift (SURVEY 8d)"
 NCU_TRAFFIC_BYTES = None   # filled from profiles/ by _ncu_traffic()
 STEP_SYNC = os.environ.get("ALIGNSDF_BENCH_STEP_SYNC", "0") == "1"
 
 
+NCU_TRAFFIC_FILES = ("r02_ncu_tc_eval_256.txt", "r01_ncu_tc3_eval_256.txt")
+
+
 def _ncu_traffic():
     """dram bytes (read + write) per 256^3 launch of the dominant kernel, from the committed ncu summary."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_tc3_eval_256.txt")
-    if not os.path.exists(path):
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in NCU_TRAFFIC_FILES) if os.path.exists(q)), None)
+    if path is None:
         return None
     tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for line in open(path):
@@ -110,7 +118,7 @@ def cpu_reference_rate(N, chunks, warm=1):
     from alignsdf_b200 import synthetic
     from oracle import alignsdf_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
-    dec = synthetic.make_decoder(0)
+    dec = synthetic.make_decoder(0, init=DECODER_INIT)
     s = synthetic.make_sample(0)
     sd = {k: v.detach() for k, v in dec.state_dict().items()}
     cfg = orc.decoder_cfg(dec)
@@ -137,10 +145,10 @@ def run_reference(args):
     line = dict(
         metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=rate, unit="Mq/s",
         impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-        ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+        ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None, dtype="f32",
         data="synthetic",
-        config=dict(workload=f"{args.N}^3 hand+obj, 2 passes + 2 marching cubes, {N_SAMPLES} synthetic latents/poses",
-                    decoder="SeparateDecoder 5x512, both/9", chunk=2 ** 18),
+        config=dict(workload=f"{args.N}^3 hand+obj, 2 passes + 2 marching cubes, {args.samples} synthetic latents/poses",
+                    decoder=DECODER_DESC, chunk=2 ** 18),
         cpu_baseline=dict(value=rate, unit="Mq/s", cores=cores, kind="port",
                           sample=f"{args.steps} chunks of 2^18 grid points of the {args.N}^3 workload through "
                                  "the oracle port of the reference's torch-CPU path (marching cubes excluded: "
@@ -160,8 +168,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--N", type=int, default=256)
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--cpu-chunks", type=int, default=6, help="chunks of 2^18 points for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true",
+                    help="N > 1: assert the z-slab mesh of sample 0 equals the single-GPU mesh bit for bit")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,12 +193,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     N = args.N
     W, K = max(args.warmup, 3), args.steps
+    S = max(1, min(args.samples, W + K))         # distinct samples actually visited
 
-    dec = synthetic.make_decoder(0)
+    dec = synthetic.make_decoder(0, init=DECODER_INIT)
     host_samples = []
-    for i in range(N_SAMPLES):                 # per-step inputs live in PINNED host memory
-        s = synthetic.make_sample(i)
-        pin = lambda t: t.contiguous().pin_memory()
+    pin = lambda t: t.contiguous().pin_memory()
+    for s in synthetic.make_batch(S):           # per-step inputs live in PINNED host memory
         host_samples.append(synthetic.Sample(pin(s.latent), {k: pin(v) for k, v in s.mano_results.items()},
                                              {k: pin(v) for k, v in s.obj_results.items()}, s.specs))
     h2d_bytes = sum(t.numel() * 4 for t in [host_samples[0].latent, *host_samples[0].mano_results.values(),
@@ -199,67 +210,80 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    kernel_ms = []
-
     def step_device(i, bound):
         """Device-resident step: 2 passes + 2 marching cubes (+ slab collectives when world > 1)."""
         if world == 1:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            mask = 3
-            ev0.record()
-            h1, o1, _, box = bound.eval_grid(N, 2.0 / (N - 1), [-1.0, -1.0, -1.0], bbox_mask=mask)
-            ev1.record()
-            mn, mx = amesh._bbox_to_minmax(box, True, True)
-            voxel, origin = amesh._regrid(mn, mx, N, 2.0 / (N - 1))
-            h2, o2, _, _ = bound.eval_grid(N, float(voxel), origin.tolist())
-            vs = float(voxel)
-            for vol in (h2, o2):
-                engine.marching_cubes(vol.view(N, N, N), 0.0, [vs] * 3, origin.tolist(), check_range=False)
-            kernel_ms.append((ev0, ev1))
+            r = amesh._two_pass_verified(bound, N, 3, "reference", False)
+            g = r["grid"][0].tolist()
+            for vol in (r["hand"], r["obj"]):
+                engine.marching_cubes(vol[0].view(N, N, N), 0.0, [g[0]] * 3, g[1:4], check_range=False)
         else:
-            be = slab.gpu_backend(bound, N)
-            fields = slab.two_pass_slab(be, N, rank, world)
-            slab.mesh_slab(be, fields, N, rank, world)
+            slab.reconstruct_slab(slab.gpu_backend(bound, N), N, rank, world)
             if STEP_SYNC:
                 torch.cuda.synchronize(dev)
 
     def bind(i):
-        s = host_samples[i % N_SAMPLES].to(dev)
+        s = host_samples[i % S].to(dev)
         return eng.bind(s.latent, s.specs, s.mano_results, s.obj_results)
 
     # ---------------- device-resident timing ----------------
-    bounds = [bind(i) for i in range(N_SAMPLES)]
-    # untimed set-up: one pass over the batch, so that every sample's packed blocks exist and the caching
-    # allocator has seen every (sample-dependent) mesh buffer size -- otherwise the first visit of each sample,
-    # inside the timed region, pays cudaMalloc + device synchronisation on every rank (multi-rank runs varied
-    # between 27 and 50 ms per step at 4 GPUs, while the end-to-end leg that runs afterwards was stable)
-    for i in range(N_SAMPLES):
+    bounds = [bind(i) for i in range(S)]
+    # untimed set-up: one pass over the batch, so that every sample's packed blocks and calibration exist and the
+    # caching allocator has seen every (sample-dependent) mesh buffer size -- otherwise the first visit of each
+    # sample, inside the timed region, pays cudaMalloc + device synchronisation on every rank
+    for i in range(S):
         step_device(i, bounds[i])
     for i in range(W):
-        step_device(i, bounds[i % N_SAMPLES])
-    kernel_ms.clear()
+        step_device(i, bounds[i % S])
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
+    engine.KERNEL_EVENTS, engine.MC_EVENTS = [], []
     l0 = engine.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        step_device(i, bounds[i % N_SAMPLES])
+        step_device(i, bounds[i % S])
     e1.record()
     barrier()
     launches = engine.LAUNCHES["count"] - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    k1_ms = [a.elapsed_time(b) for a, b in kernel_ms]
+    k1 = {}
+    for kind, nq, a, b in engine.KERNEL_EVENTS:
+        if nq >= N ** 3 // max(world, 1) // 2:          # grid passes only (not the calibration launches)
+            k1.setdefault(kind, []).append((a.elapsed_time(b), nq))
+    mc = [(nb, a.elapsed_time(b) + c.elapsed_time(d)) for nb, a, b, c, d in engine.MC_EVENTS]
+    engine.KERNEL_EVENTS = engine.MC_EVENTS = None
+    kinds_used = sorted(set().union(*[b.kinds_used for b in bounds]))
+    product_kind = engine.LEVEL_NAMES[eng.level]
+
+    # ---------------- 16 samples in ONE launch per pass (config #3; single GPU) ----------------
+    batched = None
+    if world == 1 and S >= 2 and N <= 256:
+        SB = min(S, 16)
+        bb = eng.bind_batch([(s.latent, s.specs, s.mano_results, s.obj_results) for s in (h.to(dev) for h in host_samples[:SB])])
+        for _ in range(2):
+            r = amesh._two_pass_verified(bb, N, 3, "reference", False)
+        torch.cuda.synchronize(dev)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        r = bb.two_pass(N, 3, "reference", eng.level if eng.level < engine.LEVEL_SIMT else None, False)
+        b1.record()
+        torch.cuda.synchronize(dev)
+        bms = b0.elapsed_time(b1)
+        batched = dict(samples_per_launch=SB, ms_two_passes=bms, Mq_per_s=2.0 * N ** 3 * SB / (bms * 1e-3) / 1e6,
+                       note="both grid passes of the whole batch as two launches (P-tile base indexed by sample), "
+                            "marching cubes not included")
+        del r, bb
 
     # ---------------- end-to-end through the public API ----------------
     tmp = tempfile.mkdtemp(prefix="asdf_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     d2h_bytes = [0]
 
     def step_e2e(i):
-        s = host_samples[i % N_SAMPLES].to(dev)          # H2D of this step's inputs (pinned -> device)
+        s = host_samples[i % S].to(dev)          # H2D of this step's inputs (pinned -> device)
         prefix = os.path.join(tmp, f"s{rank}_{i % 2}")
         if world == 1:
             res = amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results,
@@ -279,22 +303,42 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---------------- end-to-end, batch API (single GPU): host stages overlapped across samples ----------------
-    e2e_pipe_s = None
-    if world == 1:
-        names = [os.path.join(tmp, f"p{i % 2}") for i in range(K + 2)]
-        amesh.create_meshes_pipelined(dec, [host_samples[i % N_SAMPLES] for i in range(2)], names[:2], N=N)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        amesh.create_meshes_pipelined(dec, [host_samples[i % N_SAMPLES] for i in range(K)], names[:K], N=N)
-        torch.cuda.synchronize(dev)
-        e2e_pipe_s = time.perf_counter() - t0
+    # ---------------- end-to-end, batch API: host stages overlapped across samples ----------------
+    # world == 1: the K samples of the step loop.  world > 1: SAMPLE-PARALLEL mode (dist_reconstruct.py:63-84):
+    # rank r reconstructs samples r, r + world, ... of the same K on its own GPU, no communication.
+    mine = list(range(rank, K, world))
+    names = [os.path.join(tmp, f"p{rank}_{j % 2}") for j in range(len(mine) + 2)]
+    amesh.create_meshes_pipelined(dec, [host_samples[i % S] for i in range(2)], names[:2], N=N, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    if mine:
+        amesh.create_meshes_pipelined(dec, [host_samples[i % S] for i in mine], names[:len(mine)], N=N, device=dev)
+    torch.cuda.synchronize(dev)
+    e2e_pipe_s = time.perf_counter() - t0
+
+    check = None
+    if args.check and world > 1:
+        s = host_samples[0].to(dev)
+        a = slab.create_mesh_combined_decoder_slab(True, True, False, dec, s.latent, s.mano_results, s.obj_results,
+                                                   None, s.specs, os.path.join(tmp, "chk_slab"), N=N)
+        if rank == 0:
+            b = amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results, s.obj_results,
+                                                   None, s.specs, os.path.join(tmp, "chk_one"), N=N)
+            import numpy as np
+            check = all(a[t] is not None and b[t] is not None and np.array_equal(a[t].vertices, b[t].vertices)
+                        and np.array_equal(a[t].faces, b[t].faces) for t in ("hand", "obj"))
+            same_files = all(open(os.path.join(tmp, f"chk_slab_{t}.ply"), "rb").read() ==
+                             open(os.path.join(tmp, f"chk_one_{t}.ply"), "rb").read() for t in ("hand", "obj"))
+            check = dict(slab_mesh_equals_single_gpu=bool(check), ply_bytes_equal=bool(same_files),
+                         faces={t: int(b[t].faces.shape[0]) for t in ("hand", "obj")})
+            assert check["slab_mesh_equals_single_gpu"] and check["ply_bytes_equal"], check
+        barrier()
 
     # ---------------- max over ranks ----------------
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, pipe_ms = float(t[0]), float(t[1]), float(t[2])
     queries = 2.0 * N ** 3 * K
     value = queries / (ms * 1e-3) / 1e6
     e2e_value = queries / (e2e_ms * 1e-3) / 1e6
@@ -303,35 +347,58 @@ def main():
         global NCU_TRAFFIC_BYTES
         NCU_TRAFFIC_BYTES = _ncu_traffic() if N == 256 else None
         peaks = measured_peaks()
+        dtype = {"f16+2xe4m3": "f16 main + 2 e4m3 correction products (fp32 accumulate)",
+                 "f16x3": "3 f16 products (hi*hi + lo*hi + hi*lo, fp32 accumulate)", "simt": "f32"}[product_kind]
         line = dict(
             metric="hand+obj SDF queries/s (2-pass grid + marching cubes)", value=value, unit="Mq/s",
             n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
-            scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f16 main + 2 e4m3 correction products (fp32 accumulate)",
+            scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype=dtype,
             data="synthetic", impl="b200",
-            config=dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {N_SAMPLES} synthetic latents/poses",
-                        decoder="SeparateDecoder 5x512, both/9", parallelism=f"zslab{world}" if world > 1 else "single",
+            config=dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {args.samples} synthetic latents/poses",
+                        decoder=DECODER_DESC, parallelism=f"zslab{world}" if world > 1 else "single",
+                        samples_visited=S,
                         l2="outputs (2 x 67 MB per pass) exceed L2; the 4 MB weight stream is L2-resident by design",
                         meshes_per_s=K / (ms * 1e-3), decoder_evals_Mps=2 * value),
+            kernel=dict(selected=product_kind, kinds_launched=kinds_used, calibration_err=eng.calib,
+                        stats=dict(engine.STATS)),
             e2e=dict(value=e2e_value, unit="Mq/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes[0],
                      ms_per_step=e2e_ms / K, meshes_per_s=K / (e2e_ms * 1e-3)),
             gpu_launches=launches, clocks=clocks)
-        if e2e_pipe_s is not None:
-            line["e2e"]["pipelined_batch"] = dict(
-                value=queries / e2e_pipe_s / 1e6, unit="Mq/s", ms_per_step=e2e_pipe_s * 1e3 / K,
-                api="mesh.create_meshes_pipelined: same files, consecutive samples overlapped (host inputs, PLY written)")
-        if world == 1 and k1_ms:
-            k1 = sum(k1_ms) / len(k1_ms)
-            ach = N ** 3 * F_MIN / (k1 * 1e-3) / 1e12
-            # issued tensor work in fp16-MMA time: padded shapes x (1 fp16 product + 2 fp8 products at twice the rate)
-            issued = ach * 2 * (2 * 2 * 524288) / F_MIN
-            line["roofline"] = dict(bound="tensor", kernel="tc3_eval_kernel", achieved=ach, peak=peaks["tflops"],
+        pipe = dict(value=queries / (pipe_ms * 1e-3) / 1e6, unit="Mq/s", ms_per_step=pipe_ms / K,
+                    meshes_per_s=K / (pipe_ms * 1e-3),
+                    api="mesh.create_meshes_pipelined: same files, consecutive samples overlapped (host inputs, PLY written)")
+        if world == 1:
+            line["e2e"]["pipelined_batch"] = pipe
+        else:
+            pipe["mode"] = (f"sample-parallel (dist_reconstruct.py:63-84): {K} samples dealt round-robin to {world} ranks, "
+                            "no communication, end to end, max over ranks")
+            line["sample_parallel"] = pipe
+        if batched is not None:
+            line["batched"] = batched
+        if check is not None:
+            line["check"] = check
+        if k1:
+            kind = max(k1, key=lambda k: len(k1[k]))
+            tms = sum(t for t, _ in k1[kind]) / len(k1[kind])
+            nq = sum(q for _, q in k1[kind]) / len(k1[kind])
+            ach = nq * F_MIN / (tms * 1e-3) / 1e12
+            # issued tensor work in fp16-MMA time on padded shapes: 3 fp16 products, or 1 fp16 + 2 fp8 at twice the rate
+            issued = ach * (2.0 if kind == "f16+2xe4m3" else 3.0) * (2 * 2 * 524288) / F_MIN
+            line["roofline"] = dict(bound="tensor", kernel=f"tc_eval_kernel<{kind}>", achieved=ach, peak=peaks["tflops"],
                                     unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=NCU_TRAFFIC_BYTES,
                                     traffic_note="dram__bytes_read+write of one 256^3 launch, ncu --set full "
-                                                 "(profiles/r01_ncu_tc3_eval_256.txt); algorithmic HBM bytes = 8 B/query",
-                                    ms_per_launch=k1, queries_per_launch=N ** 3, flop_per_query=F_MIN,
-                                    issued_tflops_f16_equiv=issued, fallbacks_to_fp16_kernel=engine.STATS["f8_rejected"],
-                                    frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
-                                    Mq_per_s_kernel=N ** 3 / (k1 * 1e-3) / 1e6)
+                                                 "(profiles/); algorithmic HBM bytes = 8 B/query",
+                                    ms_per_launch=tms, queries_per_launch=nq, flop_per_query=F_MIN,
+                                    issued_tflops_f16_equiv=issued, frac_of_burst=ach / peaks["tflops_burst"],
+                                    peak_source=peaks["source"], Mq_per_s_kernel=nq / (tms * 1e-3) / 1e6,
+                                    other_kinds={k: sum(t for t, _ in v) / len(v) for k, v in k1.items() if k != kind})
+        if mc:
+            nb = sum(b for b, _ in mc) / len(mc)
+            tm = sum(t for _, t in mc) / len(mc)
+            line["roofline_mc"] = dict(bound="hbm", kernel="mc_classify + mc_scan_* + mc_compact + mc_emit",
+                                       achieved=nb / (tm * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                                       frac=nb / (tm * 1e-3) / 1e9 / peaks["hbm"], bytes_alg_per_surface=nb,
+                                       ms_per_surface=tm, formula="4 N^3 + 12 V + 12 F per surface")
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores = cpu_reference_rate(N, args.cpu_chunks)
             line["cpu_baseline"] = dict(value=rate, unit="Mq/s", cores=cores, kind="port",

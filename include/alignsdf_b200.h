@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ASDF_ABI_VERSION 2
+#define ASDF_ABI_VERSION 3
 #define ASDF_MAX_LAYERS 8
 #define ASDF_MAX_POINT_DIM 64
 
@@ -173,11 +173,15 @@ typedef struct {
   float iso;
   double spacing[3];
   float origin[3];         /* points = origin + verts (utils/mesh.py:360-363) */
+  const float* grid_dev;   /* optional: f32[4] = {voxel, origin x3} on the device (a row of asdf_regrid's output); when
+                            * non-NULL it replaces spacing (all three axes) and origin, so that marching cubes can be
+                            * queued behind the grid passes without a host round trip */
 } asdf_mc_params;
 size_t asdf_mc_scratch_bytes(const asdf_mc_params* p);
-/* Pass 1: classify + count + scan (the field is read once).  totals_dev: int64[5] = {n_verts, n_tris, min_bits,
- * max_bits, n_segments} (field min/max as ordered-int bit patterns, for the "level outside data range" check;
- * n_segments = runs of 32 grid points that own a vertex or a triangle, handed back to asdf_mc_emit). */
+/* Pass 1: classify + count + scan (the field is read once).  totals_dev: int64[5] = {n_verts, n_tris, 0, 0,
+ * n_segments} (n_segments = runs of 32 grid points that own a vertex or a triangle, handed back to asdf_mc_emit).
+ * n_verts == 0 means the field never crosses iso; whether iso lies outside [min, max] (skimage's ValueError, caught
+ * at utils/mesh.py:353-358) is then the caller's reduction -- the streaming pass carries none. */
 int asdf_mc_count(const float* vol_dev, const asdf_mc_params* p, void* scratch_dev,
                   int64_t* totals_dev, void* stream);
 /* Pass 2: emit.  verts_dev [V,3] f32 (array-axis order * spacing, what marching_cubes returns),

@@ -39,16 +39,37 @@ def _oracle_backend(dec, sample, N):
                     box[6 * bi + 3:6 * bi + 6] = ijk.max(0).values.int()
         return h, o, box
 
-    def mc(vol, voxel, origin, z0):
+    from alignsdf_b200 import mesh as amesh
+    vs1 = 2.0 / (N - 1)
+    zeros = lambda: torch.zeros(slab.N_FLAGS, dtype=torch.int32)
+
+    def pass1(begin, end, mask):
+        _, _, box = ev(begin, end, vs1, [-1.0, -1.0, -1.0], mask)
+        if box is None:                                   # empty slab (more ranks than planes)
+            box = torch.tensor([slab.INT_MAX] * 3 + [-1] * 3 + [slab.INT_MAX] * 3 + [-1] * 3, dtype=torch.int32)
+        return box, zeros()
+
+    def regrid(box, mask):
+        mn, mx = amesh._bbox_to_minmax(box, bool(mask & 1), bool(mask & 2))
+        voxel, origin = amesh._regrid(mn, mx, N, vs1)
+        return torch.cat([voxel.reshape(1), origin]).float()
+
+    def pass2(begin, end, grid):
+        h, o, _ = ev(begin, end, float(grid[0]), grid[1:4].tolist(), 0)
+        return h, o, zeros()
+
+    def mc_count(vol, grid, z0):
         try:
-            v, f, k = mo.marching_cubes(vol.numpy(), 0.0, [voxel] * 3, (z0, 0, 0), (N, N, N))
+            v, f, k = mo.marching_cubes(vol.numpy(), 0.0, [float(grid[0])] * 3, (z0, 0, 0), (N, N, N))
         except ValueError:
             v, f, k = np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32), np.zeros(0, np.uint64)
-        p = (np.asarray(origin, np.float32)[None] + v).astype(np.float32)
-        return (torch.from_numpy(v), torch.from_numpy(p), torch.from_numpy(f),
-                torch.from_numpy(k.astype(np.int64)))
+        return torch.tensor([len(v), len(f), 0, 0, 1], dtype=torch.int64), (v, f, k)
 
-    return slab.Backend(ev, mc, torch.device("cpu"))
+    def mc_emit(handle, nv, nt, nseg):
+        v, f, k = handle
+        return torch.from_numpy(v), torch.from_numpy(f), torch.from_numpy(k.astype(np.int64))
+
+    return slab.Backend(pass1, regrid, pass2, mc_count, mc_emit, torch.device("cpu"))
 
 
 def _worker(rank, world, port, name, out_dir):
@@ -61,11 +82,12 @@ def _worker(rank, world, port, name, out_dir):
         N = meta["N"]
         be = _oracle_backend(dec, sample, N)
         be.relief = 2 if world == 3 else 0          # uneven slabs must give the identical result
-        fields = slab.two_pass_slab(be, N, rank, world)
-        meshes = slab.mesh_slab(be, fields, N, rank, world)
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=float(fields["voxel"]),
-                 origin=fields["origin"].numpy(), hand=fields["hand"].numpy(), z0=fields["z0"], z1=fields["z1"])
+        res = slab.reconstruct_slab(be, N, rank, world, keep_fields=True)
+        grid = res["grid"].numpy()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=grid[0], origin=grid[1:4], hand=res["hand"].numpy(),
+                 z0=res["z0"], z1=res["z1"])
         if rank == 0:
+            meshes = res["meshes"]
             np.savez(os.path.join(out_dir, "mesh.npz"),
                      **{f"{t}_{n}": a.numpy() for t in meshes for n, a in zip(("v", "p", "f"), meshes[t])})
         dist.barrier()          # rank 0 may still be receiving the gathered pieces
@@ -87,7 +109,7 @@ def test_slab_planes_partition():
         assert cuts[0][1] - cuts[0][0] == max(N // w - relief, 1)
         rest = [b - a for a, b in cuts[1:]]
         assert max(rest) - min(rest) <= 1
-    assert slab.default_relief(256, 8) == 3 and slab.default_relief(256, 2) == 2 and slab.default_relief(32, 8) == 0
+    assert slab.default_relief(256, 8) == 2 and slab.default_relief(256, 2) == 1 and slab.default_relief(32, 8) == 0
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -14,8 +14,8 @@ from alignsdf_b200 import mesh as amesh, synthetic  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dev = torch.device("cuda")
-dec = synthetic.make_decoder(0)
-samples = [synthetic.make_sample(i) for i in range(4)]
+dec = synthetic.make_decoder(0, init=os.environ.get("E2E_DECODER", "default"))
+samples = synthetic.make_batch(4)
 tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
 
 
@@ -40,4 +40,4 @@ for i in range(4):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("cumulative").print_stats(28)
+st.sort_stats("cumulative").print_stats(45)
