@@ -63,13 +63,16 @@ constexpr int kRows = 128;                  // points per CTA
 constexpr int kPtsPerTile = 256;            // per CTA pair
 constexpr int kTileBytes = 64 * 64 * 2;     // weight tile: 64 rows x 64 k fp16, or 64 rows x (64 + 64) e4m3 = 8 KiB
 constexpr int kSlotBytes = kRows * 128;     // ALO slot: 128 rows x (64 lo8 + 64 x8 | 64 lo16) = 16 KiB
-constexpr int kRing = 10;                   // ring slots of one 8 KiB tile each
+constexpr int kRing = 10;                   // ring: 10 slots of one 8 KiB tile (F16X3) or 5 slots of a 16 KiB (hi, correction) pair (F16_F8)
 constexpr int kChunksPerDecoder = 64;       // 64-wide K chunks of all N blocks: 16 (L1) + 16 (L2) + 32 (L3)
 constexpr int kPTilesPerDecoder = 14;       // 4 (L0) + 2 (L1) + 4 (L2) + 4 (L3) N blocks
 // weight tiles per 64-wide K chunk: the correction tiles of the chunk (F16X3: hi16(W) and lo16(W); F16_F8: the
 // [W8 | Wl8] tile) come in the block's correction phase, the hi16(W) tile again in its main phase
 __host__ __device__ constexpr int tiles_per_chunk(bool f8) { return f8 ? 2 : 3; }
-__host__ __device__ constexpr int fills_per_instance(bool f8) { return kChunksPerDecoder * tiles_per_chunk(f8) + kPTilesPerDecoder; }
+// ring fills per decoder instance: F16X3 one per tile, F16_F8 one per (hi, correction) pair; + the P tiles
+__host__ __device__ constexpr int fills_per_instance(bool f8) { return kChunksPerDecoder * (f8 ? 1 : 3) + kPTilesPerDecoder; }
+__host__ __device__ constexpr int ring_slots(bool f8) { return f8 ? kRing / 2 : kRing; }
+__host__ __device__ constexpr int ring_slot_bytes(bool f8) { return f8 ? 2 * kTileBytes : kTileBytes; }
 __host__ __device__ constexpr int64_t weight_bytes_per_decoder(bool f8) {          // [rank][tile]
   return (int64_t)2 * kChunksPerDecoder * tiles_per_chunk(f8) * kTileBytes;
 }
@@ -244,6 +247,10 @@ __device__ __forceinline__ int buf_of(int g) { return g < 3 ? 0 : (g == 3 ? 1 : 
 
 template <bool kF8, bool kDebug>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval_kernel(const Args a) {
+  // accumulation order inside an N block: F16X3 corrections first (accumulator truncation), F16_F8 interleaved
+  // (shared-memory operand bandwidth); the packed weight stream (tc_pack.py) follows the same order
+  constexpr bool kCorrFirst = !kF8;
+  constexpr int kSlots = ring_slots(kF8), kSlotStride = ring_slot_bytes(kF8);
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
@@ -290,16 +297,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
     // Pushes tiles in exactly the order the issuer consumes them (see the schedule above).
     if (lane == 0 && n_inst > 0) {
       uint32_t slot = 0, phase = 0;
-      auto push = [&](const uint8_t* src) {
+      auto push = [&](const uint8_t* src, uint32_t bytes = kTileBytes) {
         mbar_wait(bar(kBarEmpty + slot), phase ^ 1);
         const uint32_t fb = bar((leader ? kBarFull : kBarFullLocal) + slot);
         if (kDebug && (a.dbg_flags & 2)) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(fb) : "memory");
         } else {
-          mbar_expect_tx(fb, kTileBytes);
-          bulk_g2s(sbase + kOffRing + slot * kTileBytes, src, kTileBytes, fb);
+          mbar_expect_tx(fb, bytes);
+          bulk_g2s(sbase + kOffRing + slot * kSlotStride, src, bytes, fb);
         }
-        if (++slot == kRing) { slot = 0; phase ^= 1; }
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       auto ptile = [&](uint32_t smp, int dec, int g) {
         return a.samp + (int64_t)smp * a.samp_stride + ((int64_t)(dec * 2 + rank) * kPTilesPerDecoder + g) * kTileBytes;
@@ -316,10 +323,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         const uint8_t* mt = a.stat + (int64_t)(dec * 2 + rank) * (weight_bytes_per_decoder(kF8) / 2);
         for (int g = 2; g < kPTilesPerDecoder; ++g) {
           const int n = layer_chunks(nb_layer(g));
-          for (int j = 0; j < n * kCorrTiles; ++j) { push(mt); mt += kTileBytes; }    // correction phase
-          push(ptile(smp, dec, g));
-          for (int j = 0; j < n; ++j) {                                               // main phase
-            push(mt); mt += kTileBytes;
+          if (kCorrFirst) {
+            for (int j = 0; j < n * kCorrTiles; ++j) { push(mt); mt += kTileBytes; }  // correction phase
+            push(ptile(smp, dec, g));
+          } else {
+            push(ptile(smp, dec, g));
+          }
+          for (int j = 0; j < n; ++j) {                                               // main phase / (hi, correction) pairs
+            if (kCorrFirst) { push(mt); mt += kTileBytes; }
+            else { push(mt, 2 * kTileBytes); mt += 2 * kTileBytes; }                  // (hi, correction) pair in one copy
             if (g == kPTilesPerDecoder - 1 && has_next) {
               if (j == 2) push(ptile(smp_next, dec_next, 0));
               if (j == 5) push(ptile(smp_next, dec_next, 1));
@@ -339,7 +351,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         for (int i = 0; i < fills; ++i) {
           mbar_wait(bar(kBarFullLocal + slot), phase);
           mbar_arrive_cluster(bar(kBarFull + slot), 0);
-          if (++slot == kRing) { slot = 0; phase ^= 1; }
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
         }
       }
       __syncwarp();
@@ -362,15 +374,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         mbar_wait(bar0 + 8 * (kBarFull + slot), phase);
         if (kDebug) w_ring += clock64() - t0;
         tc_fence_after();
-        const uint32_t d = ring_lo + slot * (kTileBytes >> 4);
-        if (++slot == kRing) { slot = 0; phase ^= 1; }
+        const uint32_t d = ring_lo + slot * (kSlotStride >> 4);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
         return d;
       };
       // the UMMAs issued so far no longer need ring slot `rel_slot` once they retire
       uint32_t rel_slot = 0;
       auto release = [&]() __attribute__((always_inline)) {
         umma_commit_both_if(issue, bar0 + 8 * (kBarEmpty + rel_slot));
-        if (++rel_slot == kRing) rel_slot = 0;
+        if (++rel_slot == kSlots) rel_slot = 0;
       };
       // claim accumulator buffer `buf`: wait until its previous contents were drained
       auto acquire = [&](int buf) __attribute__((always_inline)) -> uint32_t {
@@ -412,14 +424,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
             umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
             continue;
           }
-          // The tensor core truncates its fp32 accumulator toward zero after every UMMA (tools/probes/
-          // acc_round_probe.cu), an error proportional to the accumulator's magnitude at that moment.  So the
-          // CORRECTION products (2^-11 of the main product) are accumulated first, while the accumulator is
-          // still tiny -- their truncation is then negligible -- and the bias / point term and the main product
-          // last: 1 + 4 nch truncations at full magnitude instead of 1 + 12 nch.
-          for (int j = 0; j < nch; ++j) {
-            // layer 3 reads x3 as it becomes available (positions 4..7 first), except in its last block
-            const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
+          // waits for the activations of K position `pos` when this is the first N block of its layer
+          auto wait_pos = [&](int pos) __attribute__((always_inline)) {
             if (first_nb) {
               const long long t0 = kDebug ? clock64() : 0;
               mbar_wait(bar0 + 8 * (kBarAFull + pos), (a_phase >> pos) & 1u);
@@ -427,25 +433,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
               a_phase ^= 1u << pos;
               tc_fence_after();
             }
-            const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
-            const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
-            if (kF8) {
-              const uint32_t b8 = take();                    // [W8 | Wl8] rows against the [lo8 | x8] rows of ALO
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b8 + ks * 2, (j | ks) ? 1u : 0u);
-              release();
-            } else {
-              const uint32_t bh = take(), bl = take();
+          };
+          // in the last block of layer 3, after chunk j: positions {0,1} / {2,3} consumed -> the next instance's
+          // layer-0 epilogues may overwrite them; and its first two layer-0 blocks are issued here, into buffer X,
+          // while this block keeps Y busy
+          auto overlap_next = [&](int j) __attribute__((always_inline)) {
+            if (last_blk && has_next) {
+              if (j == 1) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 0));
+              if (j == 3) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 1));
+              if (j == 2 || j == 5) {
+                if (j == 2 && ((s_i + 1) & dshift) == 0) wait_ap();     // next instance starts a new item
+                layer0_block((uint32_t)((s_i + 1) >> dshift) & 1u);
+              }
+            }
+          };
+          if (!kCorrFirst) {
+            // F16_F8: bias / point term, then per 64-wide K chunk the fp16 main UMMAs (A from TMEM) alternating with
+            // the e4m3 correction UMMAs (A from shared memory) -- the alternation halves the shared-memory operand
+            // reads per unit time, which a block of back-to-back SMEM-A UMMAs would saturate (53.6 vs 49 ms per
+            // 256^3 pass).  The accumulation order does not matter for this kind: its error is the 4-bit
+            // significand of the corrections, not the accumulator's truncation.
+            point_term(d_tmem, ap_sel, 0u);
+            for (int j = 0; j < nch; ++j) {
+              const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
+              wait_pos(pos);
+              const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
+              const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
+              const uint32_t bh = take(), b8 = bh + (kTileBytes >> 4);   // hi16(W) tile, [W8 | Wl8] tile against the [lo8 | x8] rows of ALO
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                if (kDebug && (a.dbg_flags & 4)) continue;
-                umma_ss16_lo(issue, d_tmem, alo + ks * 2, bh + ks * 2, (j | ks) ? 1u : 0u);      // lo16(x) . hi16(W)
-                umma_ts_lo(issue, d_tmem, ahi + ks * 8, bl + ks * 2, 1u);                        // hi16(x) . lo16(W)
+                if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, bh + ks * 2, 1u);
+                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b8 + ks * 2, 1u);
               }
               release();
-              release();
+              overlap_next(j);
             }
+            umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
+            continue;
+          }
+          // F16X3.  The tensor core truncates its fp32 accumulator toward zero after every UMMA (tools/probes/
+          // acc_round_probe.cu), an error proportional to the accumulator's magnitude at that moment.  So the
+          // CORRECTION products (2^-11 of the main product) are accumulated first, while the accumulator is
+          // still tiny -- their truncation is then negligible -- and the bias / point term and the main product
+          // last: 1 + 4 nch truncations at full magnitude instead of 1 + 12 nch.
+          for (int j = 0; j < nch; ++j) {
+            // layer 3 reads x3 as it becomes available (positions 4..7 first), except in its last block
+            const int pos = (layer == 3 && !last_blk) ? ((j + 4) & 7) : j;
+            wait_pos(pos);
+            const uint32_t ahi = tmem_u + kAhiCol + pos * 32;
+            const uint32_t alo = alo_lo + pos * (kSlotBytes >> 4);
+            const uint32_t bh = take(), bl = take();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (kDebug && (a.dbg_flags & 4)) continue;
+              umma_ss16_lo(issue, d_tmem, alo + ks * 2, bh + ks * 2, (j | ks) ? 1u : 0u);      // lo16(x) . hi16(W)
+              umma_ts_lo(issue, d_tmem, ahi + ks * 8, bl + ks * 2, 1u);                        // hi16(x) . lo16(W)
+            }
+            release();
+            release();
           }
           point_term(d_tmem, ap_sel, (kDebug && (a.dbg_flags & 4)) ? 0u : 1u);
           for (int j = 0; j < nch; ++j) {
@@ -456,16 +501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
             for (int ks = 0; ks < 4; ++ks)
               if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, bh + ks * 2, 1u);
             release();
-            if (last_blk && has_next) {
-              // positions {0,1} / {2,3} consumed -> the next instance's layer-0 epilogues may overwrite them;
-              // and its first two layer-0 blocks are issued here, into buffer X, while this block keeps Y busy
-              if (j == 1) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 0));
-              if (j == 3) umma_commit_both_if(issue, bar0 + 8 * (kBarPosFree + 1));
-              if (j == 2 || j == 5) {
-                if (j == 2 && ((s_i + 1) & dshift) == 0) wait_ap();     // next instance starts a new item
-                layer0_block((uint32_t)((s_i + 1) >> dshift) & 1u);
-              }
-            }
+            overlap_next(j);
           }
           umma_commit_both_if(issue, bar0 + 8 * (kBarTmemFull + buf));
         }

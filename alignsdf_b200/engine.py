@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 import weakref
 
 import numpy as np
@@ -277,9 +278,15 @@ class BoundSample:
         pending, self._pending = self._pending, []
         dev = self.device
         words = [torch.zeros((), dtype=torch.int32, device=dev) for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
         for lvl, st, bst in pending:
+            # the words may have been allocated on another stream (bind thread of the pipelined API) and are dropped
+            # as soon as this function returns, before the reads queued here have run: without record_stream the
+            # caching allocator would hand their memory to that stream's next allocation right away
+            st.record_stream(cur); bst.record_stream(cur)
             words[lvl] = words[lvl] | st.reshape(()) | bst.reshape(())
         if self._calib is not None and not self._calib_checked:
+            self._calib.record_stream(cur)
             cal = self._calib.to(torch.float32).view(torch.int32)
         else:
             cal = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -636,12 +643,23 @@ def ply_face_records(faces: torch.Tensor) -> torch.Tensor:
     return rec
 
 
+_STAGING = threading.local()
+
+
+def _staging(nbytes):
+    """Per-thread pinned staging buffer, grown geometrically (cudaHostAlloc is slow and serialises with the
+    device: it must not happen per mesh)."""
+    buf = getattr(_STAGING, "buf", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = _STAGING.buf = torch.empty(max(int(nbytes * 1.5), 1 << 22), dtype=torch.uint8, pin_memory=True)
+    return buf
+
+
 def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor):
     """Write the binary PLY of a mesh that lives on the GPU (same bytes as trimesh_lite.export_ply) and hand the
-    mesh back as numpy arrays.  The vertex block and the 13-byte face records (built on the device) land in ONE
-    pinned host buffer behind the header, which goes to the file in a single write; the returned arrays are views
-    of pinned memory (torch's caching host allocator recycles it once the mesh is dropped).
-    -> (vertices [V,3] f32, faces [F,3] int32)"""
+    mesh back as numpy arrays.  The vertex block, the 13-byte face records (built on the device) and the int32
+    faces land in ONE pinned staging buffer behind the header; the file is a single write of its front part.
+    -> (vertices [V,3] f32, faces [F,3] int32), copies owned by the caller"""
     _lib.require_cuda(points, "points")
     V, F = int(points.shape[0]), int(faces.shape[0])
     header = ("ply\nformat binary_little_endian 1.0\n"
@@ -649,20 +667,22 @@ def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor):
               f"element face {F}\nproperty list uchar int vertex_indices\nend_header\n").encode("ascii")
     pad = (-len(header)) % 16
     off = pad + len(header)
-    host = torch.empty(off + 12 * V + 13 * F, dtype=torch.uint8, pin_memory=True)
-    host_faces = torch.empty((F, 3), dtype=torch.int32, pin_memory=True)
+    end = off + 12 * V + 13 * F
+    f_off = (end + 15) // 16 * 16
+    host = _staging(f_off + 12 * F)
     dev = points.device
     with torch.cuda.device(dev):
         rec = ply_face_records(faces)
         host[off:off + 12 * V].copy_(points.to(torch.float32).contiguous().view(torch.uint8).reshape(-1), non_blocking=True)
-        host[off + 12 * V:].copy_(rec.reshape(-1), non_blocking=True)
-        host_faces.copy_(faces.contiguous(), non_blocking=True)
+        host[off + 12 * V:end].copy_(rec.reshape(-1), non_blocking=True)
+        host[f_off:f_off + 12 * F].copy_(faces.contiguous().view(torch.uint8).reshape(-1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     buf = host.numpy()
     buf[pad:off] = np.frombuffer(header, dtype=np.uint8)
     with open(path, "wb") as fh:
-        fh.write(buf[pad:])
-    return host[off:off + 12 * V].view(torch.float32).view(V, 3).numpy(), host_faces.numpy()
+        fh.write(buf[pad:end])
+    return (buf[off:off + 12 * V].view(np.float32).reshape(V, 3).copy(),
+            buf[f_off:f_off + 12 * F].view(np.int32).reshape(F, 3).copy())
 
 
 def select_component(points: torch.Tensor, faces: torch.Tensor, verts_local: torch.Tensor, dims, spacing):

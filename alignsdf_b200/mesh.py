@@ -145,17 +145,29 @@ def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_fi
     np.savez(npz_filename_out, points=pts, labels=labels)
 
 
-def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None):
+def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None, launched=None):
     """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags); re-runs
-    through the next safer kernel when they say so."""
-    lvl = bound.auto_level(path)
+    through the next safer kernel when they say so.  ``launched``: (level, result) of a two_pass already queued
+    by the caller (run-ahead of the pipelined batch API)."""
+    lvl, r = launched if launched is not None else (bound.auto_level(path), None)
     while True:
-        r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1)
+        if r is None:
+            r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1)
         need = bound.verify()
         if need <= lvl:
             bound.last_kind = _engine.LEVEL_NAMES[lvl]
             return r
-        lvl = need
+        lvl, r = need, None
+
+
+def _volumes_from_two_pass(r, bound, N):
+    shp = (N, N, N)
+    g = r["grid"][0].cpu()
+    mm = r["minmax"][0].cpu()
+    view = lambda t: None if t is None else t[0].view(shp)
+    return dict(pass1_hand=view(r["pass1_hand"]), pass1_obj=view(r["pass1_obj"]), hand=view(r["hand"]),
+                obj=view(r["obj"]), cls=None, voxel=g[0].clone(), origin=g[1:4].clone(),
+                min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
 
 
 def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
@@ -178,13 +190,7 @@ def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_b
     want_cls = cls_branch and eng.topo.classifier is not None
     if bound.tc_ok and not want_cls:
         # tensor-core kernel: pass 1 -> asdf_regrid -> pass 2 without a host round trip in between
-        r = _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path)
-        g = r["grid"][0].cpu()
-        mm = r["minmax"][0].cpu()
-        view = lambda t: None if t is None else t[0].view(shp)
-        return dict(pass1_hand=view(r["pass1_hand"]), pass1_obj=view(r["pass1_obj"]), hand=view(r["hand"]),
-                    obj=view(r["obj"]), cls=None, voxel=g[0].clone(), origin=g[1:4].clone(),
-                    min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
+        return _volumes_from_two_pass(_two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path), bound, N)
     h1, o1, _, box = bound.eval_grid(N, voxel_size, [-1.0, -1.0, -1.0], grid_mode, bbox_mask=mask,
                                      path=path)
     mn, mx = _bbox_to_minmax(box, hand_branch, obj_branch)
@@ -309,21 +315,63 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
         return dev, latent, mano, obj, bound, ready
 
     n = 0
+    mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
+
+    side = {}
+
+    def finish_passes(p):
+        """Host check of a sample whose two passes were queued one sample ago (the GPU is already busy with the
+        next one): its flags and lattice are read on a side stream that only waits for THAT sample's kernels.
+        Then its volumes go to the mesh worker."""
+        idx, dev, bound, lvl, r, prefix, done, small = p
+        with torch.cuda.device(dev):
+            if r is not None:
+                if dev not in side:
+                    side[dev] = torch.cuda.Stream(dev)
+                with torch.cuda.stream(side[dev]):
+                    side[dev].wait_event(done)
+                    host = small.cpu().tolist()
+                need = bound.decide([int(x) for x in host[:4]])
+                if need <= lvl:
+                    bound.last_kind = _engine.LEVEL_NAMES[lvl]
+                    g, mm = torch.tensor(host[4:8], dtype=torch.float32), torch.tensor(host[8:14], dtype=torch.float32)
+                    view = lambda t: t[0].view(N, N, N)
+                    vols = dict(hand=view(r["hand"]), obj=view(r["obj"]), voxel=g[0].clone(), origin=g[1:4].clone(),
+                                min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)
+                else:                                    # rejected: the same sample through the safer kernel, in order
+                    r = None
+            if r is None:                                # also: decoders / queries outside the tensor-core path
+                smp = samples[idx]
+                vols = sdf_volumes(decoder, bound.inputs[0][0], bound.inputs[0][2], bound.inputs[0][3], smp.specs, N,
+                                   hand_branch, obj_branch, False, dev, grid_mode, bound=bound, keep_pass1=False)
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+        work.put((idx, vols, done, prefix))
+
     try:
         with ThreadPoolExecutor(max_workers=1) as binder:
             nxt = binder.submit(bind, 0) if samples else None
+            pending = None
             for idx, prefix in enumerate(filenames[:len(samples)]):
                 if errors:
                     break
                 dev, latent, mano, obj, bound, ready = nxt.result()
                 nxt = binder.submit(bind, idx + 1) if idx + 1 < len(samples) else None
                 torch.cuda.current_stream(dev).wait_event(ready)
-                vols = sdf_volumes(decoder, latent, mano, obj, samples[idx].specs, N, hand_branch, obj_branch,
-                                   False, dev, grid_mode, bound=bound)
-                done = torch.cuda.Event()
-                done.record(torch.cuda.current_stream(dev))
-                work.put((idx, vols, done, prefix))
+                lvl, r, done, small = bound.auto_level(), None, None, None
+                if bound.tc_ok and lvl < _engine.LEVEL_SIMT:
+                    with torch.cuda.device(dev):
+                        r = bound.two_pass(N, mask, grid_mode, lvl, False)     # queued behind the previous sample's passes
+                        # flags (exact in f64: int32 words / f32 bit patterns), lattice and bbox in one small tensor
+                        small = torch.cat([bound.pending_flags().double(), r["grid"][0].double(), r["minmax"][0].double()])
+                        done = torch.cuda.Event()
+                        done.record(torch.cuda.current_stream(dev))
+                if pending is not None:
+                    finish_passes(pending)
+                pending = (idx, dev, bound, lvl, r, prefix, done, small)
                 n += 1
+            if pending is not None and not errors:
+                finish_passes(pending)
     finally:
         work.put(None)
         worker.join()

@@ -9,9 +9,13 @@ Static stream (bytes): weight tiles ``[decoder][cta rank][tiles]`` of 8 KiB, N b
                                   K position (c + 4) % 8 and that block walks the positions in natural order so
                                   that positions 0..3 are released early for the next instance's layer-0
                                   epilogues (k1_tc.cu)
-and inside an N block first the tiles of its CORRECTION phase, chunk after chunk, then the hi tiles of its MAIN
-phase (the kernel accumulates the small correction products first: the tensor core truncates its accumulator
-after every UMMA, which costs the least while the accumulator is still tiny):
+and inside an N block
+    F16X3   first the tiles of its CORRECTION phase, chunk after chunk, then the hi tiles of its MAIN phase (the
+            kernel accumulates the small correction products first: the tensor core truncates its accumulator
+            after every UMMA, which costs the least while the accumulator is still tiny);
+    F16_F8  chunk after chunk the (hi tile, correction tile) pair: main and correction UMMAs alternate (TMEM-A /
+            SMEM-A forms; back-to-back SMEM-A UMMAs would saturate the shared-memory operand path, and this kind's
+            error is the e4m3 significand, not the accumulator's truncation):
     hi tile     shared-memory image (K-major, 128B swizzle) of 64 rows x 64 k of  hi16(s_l W_l)
     correction  F16X3:  the hi tile (for lo16(x).hi16(W)) and the same image of lo16(s_l W_l) = fp16(s_l W_l - hi16(s_l W_l))
                 F16_F8: one tile of 64 rows x 128 B: bytes 0..63  = e4m3(2^-10 s_l W_l[k]),
@@ -182,15 +186,16 @@ def pack_static_numpy(topo, kind):
                         hi = blk.astype(np.float16)
                         lo = blk - hi.astype(np.float64)
                         his.append(swizzle_tile(hi).view(np.uint8))
-                        if kind == F16_F8:
-                            stream[d, c, i] = swizzle_tile8(
+                        if kind == F16_F8:               # interleaved order: (hi, correction) pair per chunk
+                            stream[d, c, i] = his[-1]
+                            stream[d, c, i + 1] = swizzle_tile8(
                                 np.concatenate([e4m3_encode(blk / LO_SCALE), e4m3_encode(lo)], 1))
-                            i += 1
+                            i += 2
                         else:
                             stream[d, c, i] = his[-1]
                             stream[d, c, i + 1] = swizzle_tile(lo.astype(np.float16)).view(np.uint8)
                             i += 2
-                    for j in range(kcs):                 # main phase
+                    for j in range(kcs if kind != F16_F8 else 0):    # main phase (F16X3 only)
                         stream[d, c, i] = his[j]
                         i += 1
             assert i == ntiles

@@ -243,10 +243,14 @@ def main():
     l0 = engine.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = [e0]
     for i in range(K):
         step_device(i, bounds[i % S])
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     e1.record()
     barrier()
+    step_ms = sorted(a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:]))
     launches = engine.LAUNCHES["count"] - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
@@ -363,7 +367,8 @@ def main():
                         stats=dict(engine.STATS)),
             e2e=dict(value=e2e_value, unit="Mq/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes[0],
                      ms_per_step=e2e_ms / K, meshes_per_s=K / (e2e_ms * 1e-3)),
-            gpu_launches=launches, clocks=clocks)
+            gpu_launches=launches, clocks=clocks,
+            step_ms=dict(min=step_ms[0], median=step_ms[len(step_ms) // 2], max=step_ms[-1]))
         pipe = dict(value=queries / (pipe_ms * 1e-3) / 1e6, unit="Mq/s", ms_per_step=pipe_ms / K,
                     meshes_per_s=K / (pipe_ms * 1e-3),
                     api="mesh.create_meshes_pipelined: same files, consecutive samples overlapped (host inputs, PLY written)")
@@ -391,6 +396,8 @@ def main():
                                     ms_per_launch=tms, queries_per_launch=nq, flop_per_query=F_MIN,
                                     issued_tflops_f16_equiv=issued, frac_of_burst=ach / peaks["tflops_burst"],
                                     peak_source=peaks["source"], Mq_per_s_kernel=nq / (tms * 1e-3) / 1e6,
+                                    ms_per_launch_minmax=[min(t for t, _ in k1[kind]), max(t for t, _ in k1[kind])],
+                                    launches_timed=len(k1[kind]),
                                     other_kinds={k: sum(t for t, _ in v) / len(v) for k, v in k1.items() if k != kind})
         if mc:
             nb = sum(b for b, _ in mc) / len(mc)

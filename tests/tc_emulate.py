@@ -106,6 +106,22 @@ def emulate(raw_static, raw_sample, xyz, kind=T.F16X3, n_dec=2, want_max=False, 
                 cols = slice(64 * c, 64 * c + 64)
                 m = mi[0]
                 his = []
+                if kind != T.F16X3:
+                    # F16_F8: bias + point term, then per chunk main and correction UMMAs alternating (4 x [K=16 fp16, K=32 e4m3])
+                    tile = T.unswizzle_tile(ptiles[d, c, pi[0]]).astype(np.float64)      # [64, 64]
+                    add(acc, cols, ap, tile[:, :16])
+                    for pos in positions:
+                        bhi = T.unswizzle_tile(main[d, c, m].view(np.float16)).astype(np.float64)
+                        b8 = T.e4m3_decode(T.unswizzle_tile8(main[d, c, m + 1])).astype(np.float64)   # [64, 128]
+                        m += 2
+                        a8 = np.concatenate([a_c1[pos], a_c2[pos]], 1)
+                        if hw:
+                            for ks in range(4):
+                                add(acc, cols, a_hi[pos][:, 16 * ks:16 * ks + 16], bhi[:, 16 * ks:16 * ks + 16])
+                                add(acc, cols, a8[:, 32 * ks:32 * ks + 32], b8[:, 32 * ks:32 * ks + 32])
+                        else:
+                            acc[:, cols] += a_hi[pos] @ bhi.T + a8 @ b8.T
+                    continue
                 for pos in positions:                                  # correction phase
                     if kind == T.F16X3:
                         bhi = T.unswizzle_tile(main[d, c, m].view(np.float16)).astype(np.float64)

@@ -213,6 +213,31 @@ def test_marching_cubes_slabs_stitch_to_the_single_gpu_mesh(dev):
     assert np.array_equal(np.concatenate(faces), full["faces"].cpu().numpy())
 
 
+@pytest.mark.parametrize("N,cuts", [(128, (0, 61, 128)), (256, (0, 30, 94, 158, 222, 256))])
+def test_slab_stitch_by_key_lookup_equals_the_full_volume_mesh(dev, N, cuts):
+    """slab.stitch (drop each slab's copies of the next slab's first-plane vertices, re-index by key look-up) on an
+    OPEN surface that leaves the volume through every face -- at sizes that run the interior-tile path of
+    mc_classify -- equals marching cubes of the whole volume."""
+    from alignsdf_b200 import slab
+    dec = synthetic.make_decoder(0, init="default")
+    s = synthetic.make_sample(0).to(dev)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N, keep_pass1=False)
+    vs, org = float(vols["voxel"]), vols["origin"].tolist()
+    for tag in ("hand", "obj"):
+        vol = vols[tag]
+        full = engine.marching_cubes(vol, 0.0, [vs] * 3, org, want_keys=True)
+        parts, bounds = [], []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            hi = min(b + 1, N)                                    # one halo plane, except on the last slab
+            p = engine.marching_cubes(vol[a:hi].contiguous(), 0.0, [vs] * 3, org, index0_offset=a, want_keys=True,
+                                      check_range=False)
+            parts.append((p["verts"], p["faces"], p["keys"]))
+            bounds.append(b * N * N * 4 if b < N else slab.INT64_MAX)
+        verts, faces = slab.stitch(parts, bounds)
+        assert torch.equal(verts, full["verts"])
+        assert torch.equal(faces, full["faces"])
+
+
 @pytest.mark.parametrize("name", ["sep_both9_n24", "comb_cls_n12", "sep_both9_n32_handonly"])
 def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
     """Public API: files written, meshes == oracle marching cubes of the GPU volumes."""
