@@ -106,6 +106,8 @@ def lib():
     L.asdf_cc_mark.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]
     L.asdf_cc_gather.restype = C.c_int
     L.asdf_cc_gather.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    L.asdf_nn_search.restype = C.c_int
+    L.asdf_nn_search.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, vp]
     if L.asdf_abi_version() != ABI_VERSION:
         raise AsdfError("ABI version mismatch between alignsdf_b200 and its shared library")
     _lib = L

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libalignsdf_b200.so")
-SOURCES = ["api.cu", "k1_simt.cu", "k1_tc.cu", "bind.cu", "mc.cu", "cc.cu"]
+SOURCES = ["api.cu", "k1_simt.cu", "k1_tc.cu", "bind.cu", "mc.cu", "cc.cu", "nn.cu"]
 # test / profiling build of the tensor-core kernel with its cycle counters and stage knock-outs
 # (asdf_tc_eval_debug); never loaded by the product path
 DEBUG_LIB = os.path.join(HERE, "libalignsdf_b200_debug.so")

@@ -258,14 +258,16 @@ class BoundSample:
             self._calib = torch.stack(errs)
         return self._calib
 
-    def auto_level(self, path=None):
+    def auto_level(self, path=None, calibrate=True):
         """Level the next launches of this batch should use.  With "auto" this starts the calibration (async) and
-        answers the decoder's current level: speculative until verify() has looked at the calibration result."""
+        answers the decoder's current level: speculative until verify() has looked at the calibration result.
+        ``calibrate=False``: the caller starts the calibration itself (two_pass queues it behind pass 1, so that
+        its host part -- folding the sample for the fp32 kernel -- overlaps the pass)."""
         path = _PATH_ALIASES.get(path, path) if path else self.engine.path
         if path in _PATH_LEVEL:
             lvl = _PATH_LEVEL[path]
         else:
-            if self.tc_ok and self.engine.level < LEVEL_SIMT:
+            if calibrate and self.tc_ok and self.engine.level < LEVEL_SIMT:
                 self._calibrate()
             lvl = self.engine.level
         return lvl if self.tc_ok else LEVEL_SIMT
@@ -394,7 +396,7 @@ class BoundSample:
         return hand, obj, cls
 
     # ------------------------------------------------------------------ the two grid passes of a batch, no host sync
-    def two_pass(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False):
+    def two_pass(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False, calibrate=None):
         """utils/mesh.py:24-120 for all S samples: pass 1 over [-1,1]^3 (bounding boxes only unless
         ``keep_pass1``), asdf_regrid on the device, pass 2 on the per-sample lattices.  Nothing here waits for
         the GPU; call verify() once the results are needed.
@@ -409,6 +411,8 @@ class BoundSample:
         q1 = make_query(_GRID_MODES[mode], N, 0, n, voxel, (-1.0, -1.0, -1.0), bbox_mask=bbox_mask)
         box = new_bbox(dev, self.S)
         p1h, p1o, _ = self.launch_tc(kind, q1, n, keep_pass1, box)
+        if (self.engine.path == "auto" if calibrate is None else calibrate) and self.engine.level < LEVEL_SIMT:
+            self._calibrate()               # (once per batch) queued behind pass 1; its host work overlaps the pass
         grid = torch.empty((self.S, 4), dtype=torch.float32, device=dev)
         minmax = torch.empty((self.S, 6), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -655,7 +659,7 @@ def _staging(nbytes):
     return buf
 
 
-def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor):
+def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor, write=True):
     """Write the binary PLY of a mesh that lives on the GPU (same bytes as trimesh_lite.export_ply) and hand the
     mesh back as numpy arrays.  The vertex block, the 13-byte face records (built on the device) and the int32
     faces land in ONE pinned staging buffer behind the header; the file is a single write of its front part.
@@ -679,8 +683,9 @@ def export_ply_from_device(path, points: torch.Tensor, faces: torch.Tensor):
         torch.cuda.current_stream(dev).synchronize()
     buf = host.numpy()
     buf[pad:off] = np.frombuffer(header, dtype=np.uint8)
-    with open(path, "wb") as fh:
-        fh.write(buf[pad:end])
+    if write:
+        with open(path, "wb") as fh:
+            fh.write(buf[pad:end])
     return (buf[off:off + 12 * V].view(np.float32).reshape(V, 3).copy(),
             buf[f_off:f_off + 12 * F].view(np.int32).reshape(F, 3).copy())
 

@@ -10,12 +10,14 @@ Differences, all additive: the functions accept CUDA tensors and keep volumes on
 device; ``create_mesh_combined_decoder`` additionally *returns* the meshes (the reference
 returns None and only writes files); ``grid_mode="regular"`` selects the intended
 (unsheared) lattice, the default reproduces the reference's lattice bit for bit.
-``eval_mode=True`` (ICP against ground-truth meshes on disk, deep_sdf/metrics) is outside
-the hot path and raises NotImplementedError.
+``eval_mode=True`` (what dist_reconstruct.py always passes) aligns every mesh to the
+ground-truth mesh on disk with the scale / translation ICP of deep_sdf/metrics/icp_trans_scale.py,
+its nearest-neighbour searches running on the GPU (alignsdf_b200/deep_sdf/metrics).
 """
 from __future__ import annotations
 
 import logging
+import os
 import time
 
 import numpy as np
@@ -25,6 +27,8 @@ from . import engine as _engine
 from .trimesh_lite import Mesh, export_ply_records, largest_watertight_component_mc, split as _split  # noqa: F401
 
 INT_MAX = 2 ** 31 - 1
+DATA_ROOT = "data"          # eval_mode reads <DATA_ROOT>/<task>/test/mesh_{hand,obj}/<id>.obj like utils/mesh.py:386-390
+ICP_RNG = None              # numpy Generator for the ICP surface samples (None: fresh entropy, like the reference)
 
 
 def _bbox_to_minmax(box, hand_branch, obj_branch):
@@ -86,9 +90,6 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
     (raw marching-cubes vertices, i.e. before the origin shift and the component filter); with
     ``raw_on_device`` those two stay CUDA tensors (create_mesh_combined_decoder only needs them on the
     host for the label pass)."""
-    if eval_mode:
-        raise NotImplementedError("eval_mode (ICP against ground-truth meshes) is outside the hot "
-                                  "path (SURVEY.md §2 #9)")
     vol = pytorch_3d_sdf_tensor
     if not isinstance(vol, torch.Tensor):
         vol = torch.as_tensor(np.asarray(vol))
@@ -114,7 +115,8 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
                 and (offset is None or not bool(np.any(np.asarray(offset)))))
     if identity:
         # vertex block + face records -> one pinned buffer -> one write; origin + verts (f32), :360-363
-        mesh_points, sel_faces_np = _engine.export_ply_from_device(ply_filename_out, sel_points, sel_faces)
+        mesh_points, sel_faces_np = _engine.export_ply_from_device(ply_filename_out, sel_points, sel_faces,
+                                                                   write=not eval_mode)
     else:
         ply_faces = _engine.ply_face_records(sel_faces).cpu().numpy()
         mesh_points = sel_points.cpu().numpy()
@@ -123,14 +125,30 @@ def convert_sdf_samples_to_ply(pytorch_3d_sdf_tensor, voxel_grid_origin, voxel_s
             mesh_points = mesh_points * scale
         if offset is not None:
             mesh_points = mesh_points + offset
-        export_ply_records(ply_filename_out, mesh_points, ply_faces)
+        if not eval_mode:
+            export_ply_records(ply_filename_out, mesh_points, ply_faces)
     if raw_on_device:
         verts, faces = out["verts"], out["faces"]
     else:
         verts = out["verts"].cpu().numpy()
         faces = sel_faces_np if whole else out["faces"].cpu().numpy()
     source_mesh = Mesh(mesh_points, sel_faces_np)
-    res = (verts, faces, np.array([0, 0, 0]), np.array([1]))
+    trans, scale = np.array([0, 0, 0]), np.array([1])
+    if eval_mode:
+        # utils/mesh.py:385-395: scale / translation ICP of the mesh onto the ground-truth mesh of the sample, the
+        # ALIGNED mesh is what gets written; both nearest-neighbour searches run on the GPU (csrc/nn.cu)
+        from .deep_sdf.metrics.icp_trans_scale import ICP_T_S
+        from .trimesh_lite import load as _load
+        mesh_dir = 'mesh_' + ply_filename_out.split('_')[-1].split('.')[0]
+        gt_mesh_name = ply_filename_out.split('/')[-1].split('_')[0] + '.obj'
+        gt_mesh_path = os.path.join(f'{DATA_ROOT}/{task}/test', mesh_dir, gt_mesh_name)
+        target_mesh = _load(gt_mesh_path, process=False)
+        icp_solver = ICP_T_S(source_mesh, target_mesh, device=vol.device)
+        icp_solver.sample_mesh(30000, 'both', ICP_RNG)
+        icp_solver.run_icp_f(max_iter=100)
+        icp_solver.export_source_mesh(ply_filename_out)
+        trans, scale = icp_solver.get_trans_scale()
+    res = (verts, faces, trans, scale)
     return res + (source_mesh,) if return_mesh else res
 
 
@@ -149,10 +167,11 @@ def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None, launche
     """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags); re-runs
     through the next safer kernel when they say so.  ``launched``: (level, result) of a two_pass already queued
     by the caller (run-ahead of the pipelined batch API)."""
-    lvl, r = launched if launched is not None else (bound.auto_level(path), None)
+    lvl, r = launched if launched is not None else (bound.auto_level(path, calibrate=False), None)
+    auto = (_engine._PATH_ALIASES.get(path, path) if path else bound.engine.path) == "auto"
     while True:
         if r is None:
-            r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1)
+            r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1, calibrate=auto)
         need = bound.verify()
         if need <= lvl:
             bound.last_kind = _engine.LEVEL_NAMES[lvl]

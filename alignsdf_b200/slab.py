@@ -284,16 +284,19 @@ def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
     def zero_flags():
         return torch.zeros(N_FLAGS, dtype=torch.int32, device=dev)
 
+    forced = engine._PATH_ALIASES.get(path, path) in engine._PATH_LEVEL or bound.engine.path != "auto"
+
     def pass1(begin, end, mask):
-        state["level"] = lvl = bound.auto_level(path)
+        state["level"] = lvl = bound.auto_level(path, calibrate=False)
         box = engine.new_bbox(dev)
-        if end <= begin:
-            return box[0], zero_flags()
-        q = engine.make_query(mode, N, begin, end, vs1, (-1.0, -1.0, -1.0), bbox_mask=mask)
-        if lvl >= engine.LEVEL_SIMT:
-            bound._launch_simt(q, end - begin, False, box[0])
-        else:
-            bound.launch_tc(engine.LEVEL_KIND[lvl], q, end - begin, False, box)
+        if end > begin:
+            q = engine.make_query(mode, N, begin, end, vs1, (-1.0, -1.0, -1.0), bbox_mask=mask)
+            if lvl >= engine.LEVEL_SIMT:
+                bound._launch_simt(q, end - begin, False, box[0])
+            else:
+                bound.launch_tc(engine.LEVEL_KIND[lvl], q, end - begin, False, box)
+        if not forced and bound.tc_ok and lvl < engine.LEVEL_SIMT:
+            bound._calibrate()              # (once per sample) queued behind pass 1: its host work overlaps the pass
         return box[0], bound.pending_flags()
 
     def regrid(box, mask):
@@ -326,8 +329,6 @@ def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
     def mc_emit(handle, nv, nt, nseg):
         r = engine.mc_emit(handle, nv, nt, nseg, want_keys=True)
         return r["verts"], r["faces"], r["keys"]
-
-    forced = engine._PATH_ALIASES.get(path, path) in engine._PATH_LEVEL or bound.engine.path != "auto"
 
     def decide(flags):
         need = bound.decide(flags)

@@ -78,6 +78,60 @@ def export_ply_records(path, vertices, face_records):
         fh.write(rec)
 
 
+def load(path, process=False):
+    """``trimesh.load(path, process=False)`` for the two formats the path meets: Wavefront OBJ (ground-truth meshes,
+    utils/mesh.py:390) and the binary little-endian PLY written by ``export_ply``.  Polygons are fan-triangulated."""
+    path = str(path)
+    if path.lower().endswith(".obj"):
+        verts, faces = [], []
+        with open(path, "r") as fh:
+            for line in fh:
+                if line.startswith("v "):
+                    verts.append([float(x) for x in line.split()[1:4]])
+                elif line.startswith("f "):
+                    idx = [int(tok.split("/")[0]) for tok in line.split()[1:]]
+                    idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+                    for k in range(1, len(idx) - 1):
+                        faces.append([idx[0], idx[k], idx[k + 1]])
+        return Mesh(np.asarray(verts, np.float64).reshape(-1, 3), np.asarray(faces, np.int64).reshape(-1, 3))
+    if path.lower().endswith(".ply"):
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        end = raw.index(b"end_header\n") + len(b"end_header\n")
+        header = raw[:end].decode("ascii").split("\n")
+        if "format binary_little_endian 1.0" not in header:
+            raise ValueError(f"{path}: only binary little-endian PLY is supported")
+        nv = next(int(l.split()[-1]) for l in header if l.startswith("element vertex"))
+        nf = next(int(l.split()[-1]) for l in header if l.startswith("element face"))
+        props = [l for l in header if l.startswith("property") and "list" not in l]
+        if len(props) != 3:
+            raise ValueError(f"{path}: expected x, y, z float vertex properties only")
+        v = np.frombuffer(raw, "<f4", nv * 3, end).reshape(nv, 3)
+        rec = np.frombuffer(raw, np.dtype([("n", "u1"), ("idx", "<i4", (3,))]), nf, end + nv * 12)
+        return Mesh(v.astype(np.float64), rec["idx"].astype(np.int64))
+    raise ValueError(f"unsupported mesh format: {path}")
+
+
+def sample_surface(mesh: Mesh, count, rng=None):
+    """``trimesh.sample.sample_surface``: ``count`` points uniformly distributed over the surface (faces picked with
+    probability proportional to their area, uniform barycentric coordinates).  -> (points [count,3] f64, face index).
+    ``rng``: a numpy Generator (the reference draws from numpy's global state, so its samples are not
+    reproducible; parity of what follows is defined for given samples)."""
+    rng = np.random.default_rng() if rng is None else rng
+    v = np.asarray(mesh.vertices, np.float64)
+    f = np.asarray(mesh.faces)
+    area = mesh.area_faces
+    cum = np.cumsum(area)
+    pick = rng.random(count) * cum[-1]
+    face_index = np.minimum(np.searchsorted(cum, pick), len(f) - 1)
+    origin = v[f[face_index, 0]]
+    e1, e2 = v[f[face_index, 1]] - origin, v[f[face_index, 2]] - origin
+    r = rng.random((count, 2))
+    flip = r.sum(1) > 1.0
+    r[flip] = 1.0 - r[flip]
+    return origin + e1 * r[:, 0:1] + e2 * r[:, 1:2], face_index
+
+
 def split(mesh: Mesh, only_watertight=True):
     """Connected components over faces sharing an edge, as sub-meshes (trimesh.graph.split)."""
     from scipy.sparse import coo_matrix

@@ -210,6 +210,14 @@ int asdf_cc_gather(const float* points_dev, const int32_t* faces_dev, int64_t V,
                    const int32_t* keep_v_dev, const int32_t* scan_v_dev, const int32_t* keep_f_dev,
                    const int32_t* scan_f_dev, float* out_points_dev, int32_t* out_faces_dev, void* stream);
 
+/* Exact nearest neighbour (float64, brute force): for every query point the index of the closest reference point
+ * (ties: smallest index) and, when dist2_dev != NULL, the squared distance.  Replaces the KDTree queries of
+ * deep_sdf/metrics/icp_trans_scale.py:36-57 (ICP scale / translation alignment, what --eval_mode runs after every
+ * mesh, utils/mesh.py:385-395) and deep_sdf/metrics/chamfer.py:217-229 (symmetric Chamfer distance).
+ * query_dev [n_query,3], ref_dev [n_ref,3] float64; idx_dev int32[n_query]; dist2_dev float64[n_query] or NULL. */
+int asdf_nn_search(const double* query_dev, int64_t n_query, const double* ref_dev, int64_t n_ref,
+                   int32_t* idx_dev, double* dist2_dev, void* stream);
+
 int asdf_abi_version(void);
 const char* asdf_last_error(void);
 /* 1 if a CUDA device with compute capability 10.x is present, else 0 (never falls back). */
