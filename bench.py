@@ -46,7 +46,7 @@ NCU_TRAFFIC_BYTES = None   # filled from profiles/ by _ncu_traffic()
 STEP_SYNC = os.environ.get("ALIGNSDF_BENCH_STEP_SYNC", "0") == "1"
 
 
-NCU_TRAFFIC_FILES = ("r02_ncu_tc_eval_256.txt", "r01_ncu_tc3_eval_256.txt")
+NCU_TRAFFIC_FILES = ("r02_ncu_tc_eval_f8_256.txt", "r01_ncu_tc3_eval_256.txt")
 
 
 def _ncu_traffic():
