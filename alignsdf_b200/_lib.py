@@ -30,12 +30,18 @@ class Query(C.Structure):
                 ("point_stride", C.c_int32), ("bbox_mask", C.c_int32)]
 
 
+class PixelAlign(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32), ("layer", C.c_int32 * 2),
+                ("point_affine", C.c_float * 12), ("cam", C.c_float * 12), ("image_size", C.c_float),
+                ("reserved", C.c_int32), ("slot_stride", C.c_int64), ("maps_dev", C.c_void_p)]
+
+
 class SimtDesc(C.Structure):
     _fields_ = [("n_branches", C.c_int32), ("n_layers", C.c_int32), ("n_outputs", C.c_int32),
                 ("pre_tanh", C.c_int32), ("n_class", C.c_int32), ("nerf_freqs", C.c_int32),
                 ("point_dim", C.c_int32 * 2),
                 ("point_index", (C.c_int32 * ASDF_MAX_POINT_DIM) * 2),
-                ("table", ((C.c_int32 * 8) * ASDF_MAX_LAYERS) * 2)]
+                ("table", ((C.c_int32 * 8) * ASDF_MAX_LAYERS) * 2), ("pa", PixelAlign)]
 
 
 class TcLaunch(C.Structure):

@@ -35,10 +35,13 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 
 // out[n][p] = relu( sum_k WxT[k][n] in[k][p] + sum_d MB[n][d] u[d][p] + MB[n][D] )   (no relu when `raw`:
 // a LayerNorm follows)
+// ``pa_map`` != nullptr: this layer sees the per-point PixelAlign latent -- add the bicubic combination
+// sum_t tap_w[t][p] * pa_map[tap_i[t][p]][n] of the projected feature map's rows (asdf_pixel_align).
 __device__ void hidden_layer(const float* __restrict__ wxt, const float* __restrict__ mb,
                              int h, int n, int npad, int has_m, int D,
                              const float* __restrict__ in, const float* __restrict__ u,
-                             float* __restrict__ out, bool raw) {
+                             float* __restrict__ out, bool raw, const float* __restrict__ pa_map = nullptr,
+                             const int* __restrict__ tap_i = nullptr, const float* __restrict__ tap_w = nullptr) {
   const int tn = threadIdx.x & 63;
   const int p0 = (threadIdx.x >> 6) * 8;
   float acc[8][8];
@@ -48,6 +51,20 @@ __device__ void hidden_layer(const float* __restrict__ wxt, const float* __restr
     const float b = nn < npad ? __ldg(mb + (size_t)nn * (D + 1) + D) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = b;
+  }
+  if (pa_map) {
+    for (int t = 0; t < 16; ++t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float w = tap_w[t * PT + p0 + i];
+        if (w != 0.f) {                              // uniform over the warp (all its lanes share p0)
+          const float* row = pa_map + (size_t)tap_i[t * PT + p0 + i] * npad + tn;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (tn + 64 * j < npad) acc[j][i] = fmaf(w, __ldg(row + 64 * j), acc[j][i]);
+        }
+      }
+    }
   }
   if (has_m) {
     for (int dd = 0; dd < D; ++dd) {
@@ -166,6 +183,59 @@ __device__ void small_head(const float* __restrict__ wxt, int ldw, const float* 
   }
 }
 
+// torch's bicubic convolution coefficients (A = -0.75) for the taps at offsets -1, 0, 1, 2 around floor(x)
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+// PixelAlign taps of query i (utils/utils.py:536-558): project, normalise to [-1,1], bicubic grid_sample with
+// align_corners=True and zero padding; a point whose projection leaves the image takes the mean feature (map row
+// fh*fw) instead.  ti / tw: this point's column of the [16][PT] tap tables.
+__device__ void pixel_align_taps(const asdf_pixel_align& pa, const asdf_query& q, int64_t i, int* ti, float* tw) {
+#pragma unroll
+  for (int t = 0; t < 16; ++t) { ti[t * PT] = 0; tw[t * PT] = 0.f; }
+  if (i >= q.end) return;
+  float x0, x1, x2;
+  if (q.mode == ASDF_QUERY_POINTS) {
+    const float* row = q.points_dev + (size_t)i * q.point_stride;
+    x0 = __ldg(row); x1 = __ldg(row + 1); x2 = __ldg(row + 2);
+  } else {
+    grid_point(i, q.N, q.mode, q.voxel, q.origin[0], q.origin[1], q.origin[2], x0, x1, x2);
+  }
+  float c[3], h[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c[r] = pa.point_affine[4 * r] * x0 + pa.point_affine[4 * r + 1] * x1 + pa.point_affine[4 * r + 2] * x2 + pa.point_affine[4 * r + 3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) h[r] = pa.cam[4 * r] * c[0] + pa.cam[4 * r + 1] * c[1] + pa.cam[4 * r + 2] * c[2] + pa.cam[4 * r + 3];
+  const float u = h[0] / h[2] / pa.image_size * 2.f - 1.f, v = h[1] / h[2] / pa.image_size * 2.f - 1.f;
+  if (!(u >= -1.f && u <= 1.f && v >= -1.f && v <= 1.f)) {       // also NaN: the mean feature (utils/utils.py:553-555)
+    ti[0] = pa.fh * pa.fw; tw[0] = 1.f;
+    return;
+  }
+  const float ix = (u + 1.f) * 0.5f * (float)(pa.fw - 1), iy = (v + 1.f) * 0.5f * (float)(pa.fh - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  float cx[4], cy[4];
+  cubic_coeffs(ix - fx, cx);
+  cubic_coeffs(iy - fy, cy);
+  const int bx = (int)fx - 1, by = (int)fy - 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = bx + k, yy = by + j;
+      if (xx >= 0 && xx < pa.fw && yy >= 0 && yy < pa.fh) {
+        ti[(4 * j + k) * PT] = yy * pa.fw + xx;
+        tw[(4 * j + k) * PT] = cy[j] * cx[k];
+      }
+    }
+}
+
 __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* act0 = smem;
@@ -174,6 +244,8 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
   float* res = u + ASDF_MAX_POINT_DIM * PTS;          // [8][PT] head outputs
   float* sdf = res + 8 * PT;                          // [2][PT]
   int* cls_s = reinterpret_cast<int*>(sdf + 2 * PT);  // [PT]
+  int* tap_i = cls_s + PT;                            // [16][PT] PixelAlign: map rows of the bicubic taps
+  float* tap_w = reinterpret_cast<float*>(tap_i + 16 * PT);   // [16][PT] and their weights
 
   const asdf_simt_desc& d = a.d;
   const asdf_query& q = a.q;
@@ -183,6 +255,10 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = q.begin + tile * PT;
+    if (d.pa.enabled) {
+      __syncthreads();
+      if (threadIdx.x < PT) pixel_align_taps(d.pa, q, base + threadIdx.x, tap_i + threadIdx.x, tap_w + threadIdx.x);
+    }
     for (int b = 0; b < d.n_branches; ++b) {
       const int D = d.point_dim[b];
       __syncthreads();
@@ -217,7 +293,10 @@ __global__ void __launch_bounds__(NT, 1) simt_eval_kernel(const SimtArgs a) {
       float* out = act1;
       for (int l = 0; l < L - 1; ++l) {
         const int32_t* t = d.table[b][l];
-        hidden_layer(a.stat + t[4], a.samp + t[5], t[0], t[1], t[2], t[3], D, in, u, out, t[6] >= 0);
+        const float* pa_map = nullptr;
+        if (d.pa.enabled && (l == d.pa.layer[0] || l == d.pa.layer[1]))
+          pa_map = d.pa.maps_dev + (size_t)(b * 2 + (l == d.pa.layer[0] ? 0 : 1)) * d.pa.slot_stride;
+        hidden_layer(a.stat + t[4], a.samp + t[5], t[0], t[1], t[2], t[3], D, in, u, out, t[6] >= 0, pa_map, tap_i, tap_w);
         __syncthreads();
         if (t[6] >= 0) {
           layer_norm_relu(out, t[1], a.stat + t[6], a.stat + t[6] + t[1]);
@@ -325,7 +404,12 @@ extern "C" int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_de
   SimtArgs a;
   a.d = *desc; a.q = *q; a.stat = static_dev; a.samp = sample_dev; a.cls = cls_dev;
   a.out_hand = out_hand_dev; a.out_obj = out_obj_dev; a.out_cls = out_cls_dev; a.out_logits = out_logits_dev; a.bbox = bbox_dev;
-  const size_t smem = (size_t)(2 * MAXW * PTS + ASDF_MAX_POINT_DIM * PTS + 8 * PT + 2 * PT + PT) * sizeof(float);
+  if (desc->pa.enabled) {
+    ASDF_REQUIRE(desc->pa.maps_dev && desc->pa.fh >= 1 && desc->pa.fw >= 1, "PixelAlign: missing feature maps");
+    ASDF_REQUIRE(desc->pa.slot_stride >= (int64_t)(desc->pa.fh * desc->pa.fw + 1) * 8, "PixelAlign: bad slot_stride");
+    ASDF_REQUIRE(q->mode != ASDF_QUERY_POINTS || q->point_stride >= 3, "PixelAlign: point rows need >= 3 columns");
+  }
+  const size_t smem = (size_t)(2 * MAXW * PTS + ASDF_MAX_POINT_DIM * PTS + 8 * PT + 2 * PT + PT + 32 * PT) * sizeof(float);
   ASDF_CUDA_CHECK(cudaFuncSetAttribute(simt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   ASDF_CUDA_CHECK(cudaGetDevice(&dev));

@@ -191,7 +191,7 @@ def _volumes_from_two_pass(r, bound, N):
 
 def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch=True,
                 obj_branch=True, cls_branch=False, device=None, grid_mode="reference", path=None, bound=None,
-                keep_pass1=True):
+                keep_pass1=True, cam_intr=None):
     """The two evaluation passes of utils/mesh.py:24-120 on the GPU.
 
     Returns dict(pass1_hand, pass1_obj, hand, obj, cls, voxel (0-dim f32 tensor),
@@ -200,7 +200,7 @@ def sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_b
     dev = _engine._device_of(latent_vec, device)
     eng = _engine.get_engine(decoder, dev)
     if bound is None:                    # ``bound``: a sample already bound by the caller (pipelined batches)
-        bound = eng.bind(latent_vec, specs, mano_results, obj_results)
+        bound = eng.bind(latent_vec, specs, mano_results, obj_results, cam_intr=cam_intr)
     voxel_size = 2.0 / (N - 1)
     mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
     if mask == 0:
@@ -233,7 +233,8 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
     ply_filename_obj = filename + "_obj"
     decoder.eval()
     vols = sdf_volumes(decoder, latent_vec, mano_results, obj_results, specs, N, hand_branch,
-                       obj_branch, cls_branch, None if device == "cpu" else device, grid_mode, keep_pass1=False)
+                       obj_branch, cls_branch, None if device == "cpu" else device, grid_mode, keep_pass1=False,
+                       cam_intr=cam_intr)
     voxel_size = vols["voxel"]
     voxel_origin = vols["origin"].tolist()
     result = {"hand": None, "obj": None}

@@ -218,13 +218,13 @@ def fold_decoder(topo: Topology, latent, specs, mano_results, obj_results,
                  feature_mode: bool = False, affine=None):
     """Fold latent (+ embedding affine unless ``feature_mode``) into the layers.  ``affine``: the result of
     ``embedding_affine`` for this sample when the caller already has it."""
-    z = latent.detach().cpu().double().numpy().reshape(-1)
     L = topo.latent_size
-    if z.shape[0] != L:
-        raise ValueError(f"latent has {z.shape[0]} entries, decoder expects {L} "
-                         "(per-point PixelAlign latents are not supported)")
     if specs.get("PixelAlign", False):
-        raise NotImplementedError("PixelAlign (per-point latent) is a 'next' row (SURVEY.md §8f)")
+        z = np.zeros(L)             # per-point latents: applied by the kernel from projected feature maps (pixel_align.py)
+    else:
+        z = latent.detach().cpu().double().numpy().reshape(-1)
+    if z.shape[0] != L:
+        raise ValueError(f"latent has {z.shape[0]} entries, decoder expects {L}")
     if feature_mode:
         A_full = np.eye(topo.point_feat_size)
         c_full = np.zeros(topo.point_feat_size)

@@ -121,12 +121,12 @@ def _piece_bytes(nv, nf):
     return (nv * (8 + 12) + nf * 12 + 7) // 8 * 8
 
 
-def gather_pieces(pieces, counts, rank: int, world: int, group=None):
-    """Bring every rank's mesh pieces to rank 0, un-padded.
+def gather_pieces(pieces, counts, rank: int, world: int, group=None, dst: int = 0):
+    """Bring every rank's mesh pieces to rank ``dst``, un-padded.
 
     pieces: list (one per surface) of (verts [V,3] f32, faces [F,3] i32, keys [V] i64) on this rank;
     counts: host int array [world, n_surfaces, 2] = (V, F) of every rank (already exchanged).
-    Returns, on rank 0, a list over ranks of such lists; None elsewhere."""
+    Returns, on rank ``dst``, a list over ranks of such lists; None elsewhere."""
     dev = pieces[0][0].device
     nbytes = [sum(_piece_bytes(int(counts[r, s_i, 0]), int(counts[r, s_i, 1])) for s_i in range(len(pieces)))
               for r in range(world)]
@@ -154,21 +154,18 @@ def gather_pieces(pieces, counts, rank: int, world: int, group=None):
             lst.append((v, f, k))
         return lst
 
-    if rank != 0:
+    if rank != dst:
         if nbytes[rank]:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, pack(), _peer(group, 0), group)]):
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, pack(), _peer(group, dst), group)]):
                 w.wait()
         return None
-    recv = {r: torch.empty(nbytes[r], dtype=torch.uint8, device=dev) for r in range(1, world) if nbytes[r]}
+    recv = {r: torch.empty(nbytes[r], dtype=torch.uint8, device=dev) for r in range(world) if r != dst and nbytes[r]}
     ops = [dist.P2POp(dist.irecv, recv[r], _peer(group, r), group) for r in recv]
     works = dist.batch_isend_irecv(ops) if ops else []
-    out = [list(pieces)]
     for w in works:
         w.wait()
     empty = torch.empty(8, dtype=torch.uint8, device=dev)
-    for r in range(1, world):
-        out.append(unpack(recv.get(r, empty), r))
-    return out
+    return [list(pieces) if r == dst else unpack(recv.get(r, empty), r) for r in range(world)]
 
 
 def stitch(parts, bounds):
@@ -200,12 +197,18 @@ def _grid_host(grid):
     return g[0].clone(), g[1:4].clone()
 
 
+def surface_owner(tag_index: int, world: int, spread: bool) -> int:
+    """Rank that stitches, filters and writes surface ``tag_index`` (0 = first requested surface): rank 0, or with
+    ``spread`` one surface per rank (hand on 0, object on 1) so that the serial tail is shared."""
+    return tag_index % world if spread else 0
+
+
 def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branch=True, obj_branch=True,
-                     which=("hand", "obj"), group=None, keep_fields=False):
+                     which=("hand", "obj"), group=None, keep_fields=False, spread=False):
     """Both evaluation passes on this rank's slab, halo exchange, marching cubes, gather and stitch.
     Returns dict(grid f32[4] device tensor (voxel, origin; identical on every rank), z0, z1,
-    meshes = {tag: (verts, points, faces)} on rank 0 (None elsewhere), and with ``keep_fields`` hand / obj
-    [nz,N,N])."""
+    meshes = {tag: (verts, points, faces)} of the surfaces this rank owns (all on rank 0 unless ``spread``; None on
+    ranks that own none), and with ``keep_fields`` hand / obj [nz,N,N])."""
     dev = backend.device
     z0, z1 = slab_planes(N, rank, world, backend.relief)
     nz = z1 - z0
@@ -252,17 +255,21 @@ def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branc
             pieces.append((torch.zeros((0, 3), dtype=torch.float32, device=dev),
                            torch.zeros((0, 3), dtype=torch.int32, device=dev),
                            torch.zeros((0,), dtype=torch.int64, device=dev)))
-    gathered = gather_pieces(pieces, counts[:, :, :2], rank, world, group)
     out = dict(grid=grid, z0=z0, z1=z1, meshes=None)
     if keep_fields:
         out.update(fields)
-    if rank == 0:
-        bounds = [slab_planes(N, r, world, backend.relief)[1] * plane * 4 if r + 1 < world else INT64_MAX
-                  for r in range(world)]
-        meshes = {}
-        for s_i, tag in enumerate(tags):
-            verts, faces = stitch([gathered[r][s_i] for r in range(world)], bounds)
-            meshes[tag] = (verts, grid[1:4].to(verts.device)[None] + verts, faces)
+    bounds = [slab_planes(N, r, world, backend.relief)[1] * plane * 4 if r + 1 < world else INT64_MAX
+              for r in range(world)]
+    owners = [surface_owner(s_i, world, spread) for s_i in range(len(tags))]
+    meshes = {}
+    for dst in sorted(set(owners)):                             # one un-padded gather per owning rank
+        mine = [s_i for s_i, o in enumerate(owners) if o == dst]
+        gathered = gather_pieces([pieces[s_i] for s_i in mine], counts[:, mine, :2], rank, world, group, dst)
+        if rank == dst:
+            for k, s_i in enumerate(mine):
+                verts, faces = stitch([gathered[r][k] for r in range(world)], bounds)
+                meshes[tags[s_i]] = (verts, grid[1:4].to(verts.device)[None] + verts, faces)
+    if meshes:
         out["meshes"] = meshes
     return out
 
@@ -340,9 +347,11 @@ def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
 
 def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,
                                       obj_results, cam_intr, specs, filename, N=256, group=None,
-                                      grid_mode="reference", write=True):
+                                      grid_mode="reference", write=True, spread=False):
     """z-slab sharded equivalent of ``mesh.create_mesh_combined_decoder`` (call on every rank of an
-    initialised process group; rank 0 writes the files and returns the meshes)."""
+    initialised process group; rank 0 writes the files and returns the meshes).  ``spread=True``: the hand surface
+    is stitched, filtered and written by rank 0 and the object surface by rank 1 (same files; each of the two ranks
+    returns the mesh it wrote, the other entry stays None) -- halves the serial tail of a sample."""
     import logging
     from . import engine
     from .trimesh_lite import Mesh, largest_watertight_component_mc
@@ -351,12 +360,14 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
     be = gpu_backend(bound, N, grid_mode)
     which = tuple(t for t, use in (("hand", hand_branch), ("obj", obj_branch)) if use)
-    res = reconstruct_slab(be, N, rank, world, hand_branch, obj_branch, which, group)
-    if rank != 0:
+    res = reconstruct_slab(be, N, rank, world, hand_branch, obj_branch, which, group, spread=spread)
+    if res["meshes"] is None:
         return None
     result = {"hand": None, "obj": None}
     vs = float(res["grid"][0])
     for tag in which:
+        if tag not in res["meshes"]:
+            continue
         verts_d, points_d, faces_d = res["meshes"][tag]
         if faces_d.shape[0] == 0:
             logging.warning("Cannot reconstruct mesh from '{}'".format(f"{filename}_{tag}.ply"))

@@ -76,14 +76,19 @@ class Sample:
     mano_results: dict | None                 # global_trans [1,16,4,4], rot_center [1,1,3]
     obj_results: dict | None                  # obj_trans [1,4,4]
     specs: dict = field(default_factory=dict)
+    cam_intr: torch.Tensor | None = None      # [1,3,4] camera projection (PixelAlign samples only)
 
     def to(self, device):
         mv = lambda d: None if d is None else {k: v.to(device) for k, v in d.items()}
-        return Sample(self.latent.to(device), mv(self.mano_results), mv(self.obj_results), self.specs)
+        return Sample(self.latent.to(device), mv(self.mano_results), mv(self.obj_results), self.specs,
+                      None if self.cam_intr is None else self.cam_intr.to(device))
 
 
 def make_sample(seed: int, latent_size=256, point_feat_size=9, encode_style="both",
-                scale_factor=SDF_SCALE_OBMAN) -> Sample:
+                scale_factor=SDF_SCALE_OBMAN, pixel_align=None) -> Sample:
+    """``pixel_align=(fh, fw)``: a PixelAlign sample (specs['PixelAlign'], utils/utils.py:536-566) -- the latent is
+    an image feature map [1, latent_size, fh, fw], with the camera intrinsics and the predicted root joint that
+    project query points into it (about a quarter of the cube projects outside the image)."""
     g = _gen(1_000_003 * (seed + 1))
     latent = (0.5 * _gauss(g, 1, latent_size)).float()
     mano = dict(global_trans=_rigid(g, 16).unsqueeze(0),
@@ -96,6 +101,17 @@ def make_sample(seed: int, latent_size=256, point_feat_size=9, encode_style="bot
         mano_out, obj_out = None, None
     else:
         mano_out, obj_out = mano, obj
+    if pixel_align is not None:
+        fh, fw = pixel_align
+        gp = _gen(3_000_017 * (seed + 1))
+        # smooth-ish feature map around the per-sample latent: what the head of the image encoder would produce
+        latent = (latent.double()[:, :, None, None] + 0.35 * _gauss(gp, 1, latent_size, fh, fw)).float()
+        joints = (0.05 * _gauss(gp, 1, 21, 3)).double()
+        joints[:, :, 2] += 0.55                                  # ~55 cm in front of the camera
+        mano_out = dict(mano_out or {}, joints=joints.float())
+        cam = torch.tensor([[[210.0, 0.0, 128.0, 0.0], [0.0, 210.0, 128.0, 0.0], [0.0, 0.0, 1.0, 0.0]]])
+        specs = dict(specs, PixelAlign=True)
+        return Sample(latent, mano_out, obj_out, specs, cam)
     return Sample(latent, mano_out, obj_out, specs)
 
 

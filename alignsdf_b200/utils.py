@@ -39,11 +39,10 @@ def decode_sdf_multi_output(decoder, latent_vector, queries, mano_results, cam_i
     returns (sdf_hand [P,1], sdf_obj [P,1], predicted_class) where predicted_class is what the reference's
     decoder returns as its third output: the raw classifier logits [P, num_class] (networks/model.py:161-162,188)
     or ``Tensor([0])`` when the decoder has no classifier head (:188,350)."""
-    if specs.get('PixelAlign', False):
-        from . import pixel_align
-        return pixel_align.decode_sdf_multi_output(decoder, latent_vector, queries, mano_results, cam_intr, specs)
     eng = _engine.get_engine(decoder, queries.device)
-    bound = eng.bind(latent_vector, specs, mano_results, None, feature_mode=True)
+    # specs['PixelAlign']: latent_vector is the image feature map, the per-point latent is sampled in the kernel
+    # from queries[:, :3] like utils/utils.py:563-566 (alignsdf_b200/pixel_align.py)
+    bound = eng.bind(latent_vector, specs, mano_results, None, feature_mode=True, cam_intr=cam_intr)
     want_cls = eng.topo.classifier is not None
     hand, obj, cls = bound.eval_points(queries, want_cls=want_cls, want_logits=want_cls)
     if obj is None:

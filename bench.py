@@ -14,7 +14,8 @@ object field.  One step therefore answers 2*N^3 hand+object SDF queries.
           per-step inputs coming from pinned host memory and the meshes read back to the host and
           written as PLY -- H2D/D2H inside the timed region.
   N > 1   z-slab sharding of every sample across the ranks (strong scaling): one all_reduce of the
-          bbox, one all_gather of the boundary planes, gather of the mesh pieces to rank 0.
+          bbox (+ kernel flags), neighbour exchange of the boundary planes, one all_gather of the sizes,
+          un-padded gather of the mesh pieces (hand surface to rank 0, object surface to rank 1).
   --impl reference   the reference's own torch-CPU path (oracle port: /root/reference cannot travel
           to the GPU box) on all host cores, on a bounded sample of the same workload.
   --samples S        number of distinct synthetic samples cycled through (16 = config #3, 1024 = config #4).
@@ -218,7 +219,7 @@ def main():
             for vol in (r["hand"], r["obj"]):
                 engine.marching_cubes(vol[0].view(N, N, N), 0.0, [g[0]] * 3, g[1:4], check_range=False)
         else:
-            slab.reconstruct_slab(slab.gpu_backend(bound, N), N, rank, world)
+            slab.reconstruct_slab(slab.gpu_backend(bound, N), N, rank, world, spread=True)
             if STEP_SYNC:
                 torch.cuda.synchronize(dev)
 
@@ -293,8 +294,9 @@ def main():
             res = amesh.create_mesh_combined_decoder(True, True, False, dec, s.latent, s.mano_results,
                                                      s.obj_results, None, s.specs, prefix, N=N)
         else:
+            # hand surface stitched / filtered / written by rank 0, object surface by rank 1
             res = slab.create_mesh_combined_decoder_slab(True, True, False, dec, s.latent, s.mano_results,
-                                                         s.obj_results, None, s.specs, prefix, N=N)
+                                                         s.obj_results, None, s.specs, prefix, N=N, spread=True)
         if res is not None:
             d2h_bytes[0] = sum(m.vertices.nbytes + m.faces.nbytes for m in res.values() if m is not None)
 
@@ -342,6 +344,9 @@ def main():
     t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nb = torch.tensor([d2h_bytes[0]], dtype=torch.int64, device=dev)       # meshes are read back by two ranks
+        dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        d2h_bytes[0] = int(nb[0])
     ms, e2e_ms, pipe_ms = float(t[0]), float(t[1]), float(t[2])
     queries = 2.0 * N ** 3 * K
     value = queries / (ms * 1e-3) / 1e6

@@ -53,6 +53,27 @@ typedef struct {
  * Replaces networks/model.py:79-188 (CombinedDecoder.forward) and :285-350
  * (SeparateDecoder.forward) together with utils/utils.py:376-430 (kinematic_embedding)
  * and :561-572 (decode_sdf_multi_output) after host-side folding (alignsdf_b200/packer.py). */
+/* PixelAlign (specs['PixelAlign'], utils/utils.py:536-558,563-566): the latent of a query point is the bicubic
+ * sample (grid_sample, align_corners=True, zero padding; the mean feature for points that project outside the image)
+ * of an image feature map at the point's projection.  Sampling is linear in the map, so the latent columns of the
+ * two layers that see the latent (layer 0 and the skip layer) are applied to the MAP once per sample:
+ *   maps_dev[branch][slot][pixel][npad]   pixel < fh*fw: (W_z F)[:, pixel];  pixel == fh*fw: W_z mean(F)
+ * and the kernel adds the 16-tap bicubic combination of those rows to the layer's pre-activations.
+ * xyz_cam = point_affine[3x4] . [x; 1] with x = the query's first three features (POINTS mode: columns 0..2 of the
+ * row, like queries[:, :3] at utils/utils.py:564) or the grid point (grid modes; the pose-align affine of the first
+ * three features folded in by the host);  [px py pz] = cam[3x4] . [xyz_cam; 1];  uv = (px, py) / pz / image_size * 2 - 1. */
+typedef struct {
+  int32_t enabled;
+  int32_t fh, fw;                           /* feature map height / width */
+  int32_t layer[2];                         /* layers receiving the latent (slot 0, 1); -1 = unused slot */
+  float point_affine[12];
+  float cam[12];
+  float image_size;
+  int32_t reserved;
+  int64_t slot_stride;                      /* floats between consecutive [pixel][npad] maps: (fh*fw + 1) * npad */
+  const float* maps_dev;
+} asdf_pixel_align;
+
 typedef struct {
   int32_t n_branches;                       /* 2: separate hand/object MLPs, 1: one MLP with n_outputs */
   int32_t n_layers;                         /* linear layers per branch */
@@ -66,6 +87,7 @@ typedef struct {
   int32_t point_index[2][ASDF_MAX_POINT_DIM]; /* column of the query row feeding u[d] */
   int32_t table[2][ASDF_MAX_LAYERS][8];     /* h, n, npad, has_M, off_static, off_sample (in floats),
                                                off_layernorm (gamma[n] | beta[n] in static_dev, -1 = none), 0 */
+  asdf_pixel_align pa;                      /* pa.enabled = 0: the latent is folded into the sample block */
 } asdf_simt_desc;
 
 /* y_l = relu(LN_l(WxT_l^T x + M_l u + B_l)) ... tanh  (LN_l = LayerNorm, eps 1e-5, only where off_layernorm >= 0:

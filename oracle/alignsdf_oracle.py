@@ -182,9 +182,32 @@ def decoder_forward(sd, cfg, inputs):
     return y[:, 0:1], y[:, 1:2], logits
 
 
-def decode_points(sd, cfg, latent, xyz, specs, mano_results, obj_results):
-    """utils/utils.py:561-572 (non-PixelAlign branch) on raw xyz."""
+def pixel_alignment(img_feat, xyz, cam_intr, mano_results, image_size, scale_factor):
+    """utils/utils.py:536-558: per-point latent = bicubic sample (align_corners=True) of the image feature map at the
+    point's projection; points projecting outside the image take the mean feature."""
+    pred_root = mano_results["joints"][:, [0]]
+    xyz = xyz.reshape((img_feat.shape[0], -1, 3))
+    xyz_cam = (xyz * 2 / scale_factor) + pred_root                       # :539
+    batch_size, n = img_feat.shape[0], xyz.shape[1]
+    homo = torch.cat([xyz_cam, torch.ones([batch_size, n, 1])], 2)
+    xy_img = torch.bmm(cam_intr, homo.transpose(1, 2)).transpose(1, 2)   # :545
+    xy_img = (xy_img[:, :, :2] / xy_img[:, :, [2]]).unsqueeze(2)
+    uv = xy_img / image_size * 2 - 1                                     # :549
+    feat = torch.nn.functional.grid_sample(img_feat, uv, align_corners=True, mode="bicubic")[:, :, :, 0].transpose(1, 2)
+    uv = uv.squeeze().reshape((-1, 2))
+    inside = (uv[:, 0] >= -1.0) & (uv[:, 0] <= 1.0) & (uv[:, 1] >= -1.0) & (uv[:, 1] <= 1.0)
+    out_mask = (~inside).reshape((batch_size, n, -1))
+    feat[torch.where(out_mask)[:2]] = img_feat.mean(3).mean(2)[torch.where(out_mask)[:1]]   # :555
+    return feat.reshape((batch_size * n, -1))
+
+
+def decode_points(sd, cfg, latent, xyz, specs, mano_results, obj_results, cam_intr=None):
+    """utils/utils.py:561-572 on raw xyz; the PixelAlign branch (:563-566) samples the latent per point from the
+    FIRST THREE embedded features (queries[:, :3]), like the reference."""
     feats = embed(xyz, specs, mano_results, obj_results)
+    if specs.get("PixelAlign", False):
+        lat = pixel_alignment(latent, feats[:, :3], cam_intr, mano_results, specs["ImageSize"][0], specs["SdfScaleFactor"])
+        return decoder_forward(sd, cfg, torch.cat([lat, feats], 1))
     inputs = torch.cat([latent.expand(xyz.shape[0], -1), feats], 1)
     return decoder_forward(sd, cfg, inputs)
 
@@ -213,7 +236,7 @@ def higher_res_cube(vol_hand, vol_obj, N, voxel_size):
 # the whole field path  (utils/mesh.py:17-120 ; deep_sdf/mesh.py:14-55)
 # ----------------------------------------------------------------------------
 def eval_volume(sd, cfg, latent, specs, mano_results, obj_results, N, voxel_size, origin,
-                mode="reference", max_batch=2 ** 18, start=0, stop=None):
+                mode="reference", max_batch=2 ** 18, start=0, stop=None, cam_intr=None):
     stop = N ** 3 if stop is None else stop
     hand = torch.empty(stop - start)
     obj = torch.empty(stop - start)
@@ -222,7 +245,7 @@ def eval_volume(sd, cfg, latent, specs, mano_results, obj_results, N, voxel_size
     while head < stop:
         end = min(head + max_batch, stop)
         xyz = grid_points(N, voxel_size, origin, mode, head, end)
-        h, o, logits = decode_points(sd, cfg, latent, xyz, specs, mano_results, obj_results)
+        h, o, logits = decode_points(sd, cfg, latent, xyz, specs, mano_results, obj_results, cam_intr)
         hand[head - start:end - start] = h[:, 0]
         obj[head - start:end - start] = o[:, 0]
         if logits is not None:
@@ -232,7 +255,7 @@ def eval_volume(sd, cfg, latent, specs, mano_results, obj_results, N, voxel_size
 
 
 def two_pass_field(sd, cfg, latent, specs, mano_results, obj_results, N,
-                   hand_branch=True, obj_branch=True, mode="reference", max_batch=2 ** 18):
+                   hand_branch=True, obj_branch=True, mode="reference", max_batch=2 ** 18, cam_intr=None):
     """Pass 1 on [-1,1]^3, bbox of sdf<0, pass 2 on the refit cube.
 
     Returns dict(pass1_hand, pass1_obj, voxel, origin, hand, obj, cls) with the
@@ -240,12 +263,12 @@ def two_pass_field(sd, cfg, latent, specs, mano_results, obj_results, N,
     with torch.no_grad():
         vs1 = 2.0 / (N - 1)
         h1, o1, _ = eval_volume(sd, cfg, latent, specs, mano_results, obj_results, N, vs1,
-                                [-1, -1, -1], mode, max_batch)
+                                [-1, -1, -1], mode, max_batch, cam_intr=cam_intr)
         h1, o1 = h1.reshape(N, N, N), o1.reshape(N, N, N)
         nv, no, mn, mx = higher_res_cube(h1 if hand_branch else None,
                                          o1 if obj_branch else None, N, vs1)
         h2, o2, c2 = eval_volume(sd, cfg, latent, specs, mano_results, obj_results, N, nv, no,
-                                 mode, max_batch)
+                                 mode, max_batch, cam_intr=cam_intr)
     return dict(pass1_hand=h1, pass1_obj=o1, voxel=nv, origin=no, min_idx=mn, max_idx=mx,
                 hand=h2.reshape(N, N, N), obj=o2.reshape(N, N, N), cls=c2.reshape(N, N, N))
 

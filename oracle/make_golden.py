@@ -75,6 +75,10 @@ CASES = [
     dict(name="sep_default_n32", kind="separate", pf=9, style="both", N=32, seed=23, init="default"),
     dict(name="comb_plain_g4_n24", kind="combined", pf=9, style="both", N=24, seed=24, init="plain", out_gain=4.0),
     dict(name="comb_default_n16", kind="combined", pf=9, style="both", N=16, seed=25, init="default"),
+    # PixelAlign (utils/utils.py:536-566): the latent is an image feature map sampled per point (bicubic); ~40 % of
+    # the cube projects outside the image and takes the mean feature
+    dict(name="sep_pa_both9_n12", kind="separate", pf=9, style="both", N=12, seed=30, pixel_align=(10, 12)),
+    dict(name="comb_pa_xyz3_n10", kind="combined", pf=3, style="nerf", N=10, seed=31, pixel_align=(7, 5)),
 ]
 
 
@@ -116,7 +120,7 @@ def run_reference_case(case):
     use_cls = bool(case.get("use_classifier", False))
     mine = synthetic.make_decoder(seed, kind, 256, pf, style, ns, use_classifier=use_cls,
                                   init=case.get("init", "engineered"), out_gain=case.get("out_gain", 1.0))
-    sample = synthetic.make_sample(seed, 256, pf, style)
+    sample = synthetic.make_sample(seed, 256, pf, style, pixel_align=case.get("pixel_align"))
 
     ref_cls = ref_model.SeparateDecoder if kind == "separate" else ref_model.CombinedDecoder
     with warnings.catch_warnings():
@@ -168,7 +172,7 @@ def run_reference_case(case):
         with tempfile.TemporaryDirectory() as td, torch.no_grad():
             ref_mesh.create_mesh_combined_decoder(
                 hb, ob, bool(case.get("cls_branch", False)), ref_dec, sample.latent,
-                sample.mano_results, sample.obj_results, None, sample.specs,
+                sample.mano_results, sample.obj_results, sample.cam_intr, sample.specs,
                 os.path.join(td, "x"), N=N, max_batch=2 ** 18)
     finally:
         ref_mesh.get_higher_res_cube = orig_cube
@@ -195,7 +199,7 @@ def run_reference_case(case):
     g1 = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
     assert np.array_equal(g1, xyz1), "oracle pass-1 grid is not bit-exact vs reference"
     res = orc.two_pass_field(sd, cfg, sample.latent, sample.specs, sample.mano_results,
-                             sample.obj_results, N, hb, ob)
+                             sample.obj_results, N, hb, ob, cam_intr=sample.cam_intr)
     assert float(res["voxel"]) == float(nv) and np.array_equal(res["origin"].numpy(), no.numpy()), \
         "oracle re-grid parameters differ from the reference"
     g2 = orc.grid_points(N, nv, no).numpy()

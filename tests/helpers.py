@@ -27,7 +27,8 @@ def load_case(name):
                                  use_classifier=meta.get("use_classifier", False),
                                  init=meta.get("init", "engineered"), out_gain=meta.get("out_gain", 1.0),
                                  bias_shift=meta.get("bias_shift"))
-    sample = synthetic.make_sample(meta["seed"], meta["latent_size"], meta["pf"], meta["style"])
+    sample = synthetic.make_sample(meta["seed"], meta["latent_size"], meta["pf"], meta["style"],
+                                   pixel_align=tuple(meta["pixel_align"]) if meta.get("pixel_align") else None)
     return meta, g, dec, sample
 
 

@@ -32,7 +32,7 @@ def test_oracle_matches_reference_golden(name):
     sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
     res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs,
                              sample.mano_results, sample.obj_results, meta["N"],
-                             meta.get("hand_branch", True), meta.get("obj_branch", True))
+                             meta.get("hand_branch", True), meta.get("obj_branch", True), cam_intr=sample.cam_intr)
     assert np.float32(float(res["voxel"])) == g["new_voxel"]
     assert np.array_equal(res["origin"].numpy(), g["new_origin"])
     for key, arr in (("pass1_hand", res["pass1_hand"]), ("pass1_obj", res["pass1_obj"]),
@@ -63,6 +63,8 @@ def test_oracle_grid_above_2_pow_24():
 def test_folded_network_matches_reference_golden(name):
     """packer.fold_decoder (latent -> bias, pose-align -> [out,3]) vs the reference (tol 1e-6)."""
     meta, g, dec, sample = helpers.load_case(name)
+    if meta.get("pixel_align"):
+        pytest.skip("per-point latents are not folded (tests/test_gpu_pixel_align.py covers the kernel path)")
     topo = packer.decoder_topology(dec)
     N = meta["N"]
     xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1])
@@ -118,11 +120,19 @@ def test_non_rigid_pose_is_rejected():
 
 def test_unsupported_variants_raise():
     s = synthetic.make_sample(0, 256, 9, "both")
-    specs = dict(s.specs, PixelAlign=True)
     dec = synthetic.make_decoder(0)
     topo = packer.decoder_topology(dec)
-    with pytest.raises(NotImplementedError):
-        packer.fold_decoder(topo, s.latent, specs, s.mano_results, s.obj_results)
+    # PixelAlign: the fold leaves the latent out (it is applied per point from projected feature maps) ...
+    br = packer.fold_decoder(topo, None, dict(s.specs, PixelAlign=True), s.mano_results, s.obj_results)
+    zero = packer.fold_decoder(topo, torch.zeros(1, 256), s.specs, s.mano_results, s.obj_results)
+    assert all(np.array_equal(a.B, b.B) for x, y in zip(br, zero) for a, b in zip(x.layers, y.layers))
+    # ... and the set-up refuses what it cannot project
+    from alignsdf_b200 import pixel_align
+    with pytest.raises(ValueError, match="feature map"):
+        pixel_align.setup(topo, s.latent, dict(s.specs, PixelAlign=True), s.mano_results, None, None, True, "cpu")
+    with pytest.raises(ValueError, match="cam_intr"):
+        pixel_align.setup(topo, torch.zeros(1, 256, 4, 4), dict(s.specs, PixelAlign=True), s.mano_results, None, None,
+                          True, "cpu")
     with pytest.raises(ValueError, match="not an affine map"):
         packer.embedding_affine(dict(s.specs, PointFeatSize=9, EncodeStyle="nerf"), None, None)
     with pytest.raises(ValueError, match="3 \\+ 6"):

@@ -49,7 +49,7 @@ def test_two_pass_fields_match_reference_golden(dev, name, path):
     s = helpers.to_cuda(sample)
     hb, ob = meta.get("hand_branch", True), meta.get("obj_branch", True)
     vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob,
-                             cls_branch="pass2_cls" in g, path=path)
+                             cls_branch="pass2_cls" in g, path=path, cam_intr=s.cam_intr)
     assert np.float32(float(vols["voxel"])) == g["new_voxel"]
     assert np.array_equal(vols["origin"].numpy(), g["new_origin"])
     for key, vol in (("pass1_hand", vols["pass1_hand"]), ("pass1_obj", vols["pass1_obj"]),

@@ -72,7 +72,7 @@ def _oracle_backend(dec, sample, N):
     return slab.Backend(pass1, regrid, pass2, mc_count, mc_emit, torch.device("cpu"))
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, spread):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -82,13 +82,15 @@ def _worker(rank, world, port, name, out_dir):
         N = meta["N"]
         be = _oracle_backend(dec, sample, N)
         be.relief = 2 if world == 3 else 0          # uneven slabs must give the identical result
-        res = slab.reconstruct_slab(be, N, rank, world, keep_fields=True)
+        res = slab.reconstruct_slab(be, N, rank, world, keep_fields=True, spread=spread)
         grid = res["grid"].numpy()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=grid[0], origin=grid[1:4], hand=res["hand"].numpy(),
                  z0=res["z0"], z1=res["z1"])
-        if rank == 0:
-            meshes = res["meshes"]
-            np.savez(os.path.join(out_dir, "mesh.npz"),
+        meshes = res["meshes"]
+        assert (meshes is not None) == (rank == 0 or (spread and rank == 1))
+        if meshes is not None:                      # hand on rank 0, object on rank 1 when the tail is spread
+            assert sorted(meshes) == (["hand", "obj"] if not spread else [("hand", "obj")[rank]])
+            np.savez(os.path.join(out_dir, f"mesh{rank}.npz"),
                      **{f"{t}_{n}": a.numpy() for t in meshes for n, a in zip(("v", "p", "f"), meshes[t])})
         dist.barrier()          # rank 0 may still be receiving the gathered pieces
     finally:
@@ -112,11 +114,11 @@ def test_slab_planes_partition():
     assert slab.default_relief(256, 8) == 2 and slab.default_relief(256, 2) == 1 and slab.default_relief(32, 8) == 0
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_two_rank_slab_reconstruction_equals_single_process(tmp_path, world):
+@pytest.mark.parametrize("world,spread", [(2, False), (3, False), (2, True)])
+def test_two_rank_slab_reconstruction_equals_single_process(tmp_path, world, spread):
     name = "sep_both9_n24"
-    port = 29500 + os.getpid() % 2000 + world
-    mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + os.getpid() % 2000 + world + 7 * spread
+    mp.spawn(_worker, args=(world, port, name, str(tmp_path), spread), nprocs=world, join=True)
     meta, g, dec, sample = helpers.load_case(name)
     N = meta["N"]
     parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
@@ -125,7 +127,9 @@ def test_two_rank_slab_reconstruction_equals_single_process(tmp_path, world):
         assert np.float32(p["voxel"]) == g["new_voxel"] and np.array_equal(p["origin"], g["new_origin"])
     hand = np.concatenate([p["hand"] for p in parts], 0)
     assert np.abs(hand - g["pass2_hand"]).max() <= 1e-6
-    m = np.load(tmp_path / "mesh.npz")
+    m = dict(np.load(tmp_path / "mesh0.npz"))
+    if spread:
+        m.update(np.load(tmp_path / "mesh1.npz"))
     sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
     with torch.no_grad():
         res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs, sample.mano_results,
