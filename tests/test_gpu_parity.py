@@ -213,6 +213,37 @@ def test_marching_cubes_slabs_stitch_to_the_single_gpu_mesh(dev):
     assert np.array_equal(np.concatenate(faces), full["faces"].cpu().numpy())
 
 
+def test_marching_cubes_512_windows_match_the_oracle(dev):
+    """BASELINE config #5 (512^3, the marching-cubes stress): the mesh of the FULL volume -- interior-tile path of
+    mc_classify, 32-bit offsets in the millions -- restricted to 40^3 windows equals the oracle's mesh of each window:
+    same vertices (keys, bit-equal positions), same triangles in the same order."""
+    N, W = 512, 40
+    dec = synthetic.make_decoder(0, init="default")
+    s = synthetic.make_sample(0).to(dev)
+    vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N, keep_pass1=False)
+    vs = float(vols["voxel"])
+    vol = vols["hand"]
+    full = engine.marching_cubes(vol, 0.0, [vs] * 3, want_keys=True)
+    keys = full["keys"].cpu().numpy().astype(np.uint64)
+    verts = full["verts"].cpu().numpy()
+    tri_keys = keys[full["faces"].cpu().numpy()]
+    assert np.all(np.diff(keys.astype(np.int64)) > 0)                      # vertex order = key order
+    host = vol.cpu().numpy()
+    rng = np.random.default_rng(3)
+    for pick in rng.choice(len(keys), 3, replace=False):
+        p = int(keys[pick] // 4)
+        c = np.array([p // (N * N), (p // N) % N, p % N])
+        lo = np.clip(c - W // 2, 0, N - W - 1)
+        sub = host[lo[0]:lo[0] + W + 1, lo[1]:lo[1] + W + 1, lo[2]:lo[2] + W + 1]
+        ov, of, ok = mo.marching_cubes(sub, 0.0, [vs] * 3, tuple(int(x) for x in lo), (N, N, N))
+        assert len(ok) > 100
+        pos = np.searchsorted(keys, ok)
+        assert np.array_equal(keys[pos], ok)
+        assert np.array_equal(verts[pos], ov)
+        inside = np.isin(tri_keys, ok).all(1)
+        assert np.array_equal(tri_keys[inside], ok[of])
+
+
 @pytest.mark.parametrize("N,cuts", [(128, (0, 61, 128)), (256, (0, 30, 94, 158, 222, 256))])
 def test_slab_stitch_by_key_lookup_equals_the_full_volume_mesh(dev, N, cuts):
     """slab.stitch (drop each slab's copies of the next slab's first-plane vertices, re-index by key look-up) on an
