@@ -34,30 +34,32 @@ INT64_MAX = 2 ** 63 - 1
 N_FLAGS = 4                    # engine.BoundSample.pending_flags()
 
 
-def slab_planes(N: int, rank: int, world: int, relief: int = 0):
+def slab_planes(N: int, rank: int, world: int, relief: int = 0, relief_ranks: int = 1):
     """Planes [z0, z1) of axis 0 owned by ``rank`` (as even as possible, contiguous).  ``relief`` planes are
-    taken off rank 0 and spread over the others: rank 0 also gathers and stitches the mesh pieces, and with
-    back-to-back samples that tail would otherwise make every other rank wait at the next collective."""
-    if relief <= 0 or world < 2:
+    taken off each of the first ``relief_ranks`` ranks and spread over the others: those ranks also stitch, filter
+    and write a surface, and with back-to-back samples that tail would otherwise make every other rank wait at
+    the next collective."""
+    relief_ranks = min(relief_ranks, world - 1)
+    if relief <= 0 or world < 2 or relief_ranks < 1:
         base, rem = divmod(N, world)
         z0 = rank * base + min(rank, rem)
         return z0, z0 + base + (1 if rank < rem else 0)
     first = max(N // world - relief, 1)
-    if rank == 0:
-        return 0, first
-    base, rem = divmod(N - first, world - 1)
-    r = rank - 1
-    z0 = first + r * base + min(r, rem)
+    if rank < relief_ranks:
+        return rank * first, (rank + 1) * first
+    base, rem = divmod(N - relief_ranks * first, world - relief_ranks)
+    r = rank - relief_ranks
+    z0 = relief_ranks * first + r * base + min(r, rem)
     return z0, z0 + base + (1 if r < rem else 0)
 
 
-def default_relief(N: int, world: int) -> int:
-    """Planes to take off rank 0 (see slab_planes): the gather + stitch tail is worth ~2 planes of two
-    passes at any N (both scale with N^2), shared with the other ranks -> 2 (world-1)/world, if slabs are thick
-    enough for it not to matter otherwise."""
+def default_relief(N: int, world: int, spread: bool = False) -> int:
+    """Planes to take off a surface-owning rank (see slab_planes): the gather + stitch tail of BOTH surfaces is worth
+    ~2 planes of two passes at any N (both scale with N^2) -- one plane per owner when the tail is spread over two
+    ranks --, if slabs are thick enough for it not to matter otherwise."""
     if world < 2 or N // world < 16:
         return 0
-    return int(round(RELIEF_PLANES * (world - 1) / world))
+    return int(round((RELIEF_PLANES / 2 if spread else RELIEF_PLANES) * (world - 1) / world))
 
 
 RELIEF_PLANES = 2.0
@@ -80,8 +82,9 @@ class Backend:
     mc_count: callable
     mc_emit: callable
     device: torch.device
-    relief: int = 0            # planes taken off rank 0 (slab_planes)
+    relief: int = 0            # planes taken off each surface-owning rank (slab_planes)
     decide: callable = None
+    relief_ranks: int = 1      # 2 when the tail is spread (hand on rank 0, object on rank 1)
 
 
 def _peer(group, r):
@@ -210,7 +213,7 @@ def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branc
     meshes = {tag: (verts, points, faces)} of the surfaces this rank owns (all on rank 0 unless ``spread``; None on
     ranks that own none), and with ``keep_fields`` hand / obj [nz,N,N])."""
     dev = backend.device
-    z0, z1 = slab_planes(N, rank, world, backend.relief)
+    z0, z1 = slab_planes(N, rank, world, backend.relief, backend.relief_ranks)
     nz = z1 - z0
     mask = (1 if hand_branch else 0) | (2 if obj_branch else 0)
     plane = N * N
@@ -258,7 +261,7 @@ def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branc
     out = dict(grid=grid, z0=z0, z1=z1, meshes=None)
     if keep_fields:
         out.update(fields)
-    bounds = [slab_planes(N, r, world, backend.relief)[1] * plane * 4 if r + 1 < world else INT64_MAX
+    bounds = [slab_planes(N, r, world, backend.relief, backend.relief_ranks)[1] * plane * 4 if r + 1 < world else INT64_MAX
               for r in range(world)]
     owners = [surface_owner(s_i, world, spread) for s_i in range(len(tags))]
     meshes = {}
@@ -277,9 +280,10 @@ def reconstruct_slab(backend: Backend, N: int, rank: int, world: int, hand_branc
 # ----------------------------------------------------------------------------
 # product backend + public entry point
 # ----------------------------------------------------------------------------
-def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
+def gpu_backend(bound, N, grid_mode="reference", path=None, spread=False) -> Backend:
     """Kernels of libalignsdf_b200.so on ``bound`` (an engine.BoundSample of ONE sample).  Nothing here waits for
-    the GPU; the kernel kind is the decoder's current level, checked through the flags (``decide``)."""
+    the GPU; the kernel kind is the decoder's current level, checked through the flags (``decide``).  ``spread``:
+    the slab sizes anticipate reconstruct_slab(..., spread=True)."""
     import ctypes as C
 
     from . import _lib, engine
@@ -342,7 +346,8 @@ def gpu_backend(bound, N, grid_mode="reference", path=None) -> Backend:
         return need > state["level"] and not forced           # a forced kind cannot be replaced: keep its results
 
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    return Backend(pass1, regrid, pass2, mc_count, mc_emit, dev, default_relief(N, world), decide)
+    return Backend(pass1, regrid, pass2, mc_count, mc_emit, dev, default_relief(N, world, spread), decide,
+                   2 if spread else 1)
 
 
 def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decoder, latent_vec, mano_results,
@@ -358,7 +363,7 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = engine._device_of(latent_vec)
     bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
-    be = gpu_backend(bound, N, grid_mode)
+    be = gpu_backend(bound, N, grid_mode, spread=spread)
     which = tuple(t for t, use in (("hand", hand_branch), ("obj", obj_branch)) if use)
     res = reconstruct_slab(be, N, rank, world, hand_branch, obj_branch, which, group, spread=spread)
     if res["meshes"] is None:

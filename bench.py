@@ -219,7 +219,7 @@ def main():
             for vol in (r["hand"], r["obj"]):
                 engine.marching_cubes(vol[0].view(N, N, N), 0.0, [g[0]] * 3, g[1:4], check_range=False)
         else:
-            slab.reconstruct_slab(slab.gpu_backend(bound, N), N, rank, world, spread=True)
+            slab.reconstruct_slab(slab.gpu_backend(bound, N, spread=True), N, rank, world, spread=True)
             if STEP_SYNC:
                 torch.cuda.synchronize(dev)
 

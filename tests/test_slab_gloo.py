@@ -81,7 +81,8 @@ def _worker(rank, world, port, name, out_dir, spread):
         meta, g, dec, sample = helpers.load_case(name)
         N = meta["N"]
         be = _oracle_backend(dec, sample, N)
-        be.relief = 2 if world == 3 else 0          # uneven slabs must give the identical result
+        be.relief = 2 if world == 3 else (1 if spread else 0)          # uneven slabs must give the identical result
+        be.relief_ranks = 2 if spread else 1
         res = slab.reconstruct_slab(be, N, rank, world, keep_fields=True, spread=spread)
         grid = res["grid"].numpy()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), voxel=grid[0], origin=grid[1:4], hand=res["hand"].numpy(),
@@ -103,15 +104,17 @@ def test_slab_planes_partition():
         assert cuts[0][0] == 0 and cuts[-1][1] == N
         assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
         assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
-    # rank-0 relief: still a contiguous partition, rank 0 thinner, the others even among themselves
-    for N, w, relief in ((256, 8, 3), (256, 2, 2), (48, 4, 3), (10, 4, 5)):
-        cuts = [slab.slab_planes(N, r, w, relief) for r in range(w)]
+    # relief: still a contiguous partition, the relieved ranks thinner, the others even among themselves
+    for N, w, relief, rr in ((256, 8, 3, 1), (256, 2, 2, 1), (48, 4, 3, 1), (10, 4, 5, 1), (256, 8, 1, 2), (64, 2, 1, 2)):
+        cuts = [slab.slab_planes(N, r, w, relief, rr) for r in range(w)]
         assert cuts[0][0] == 0 and cuts[-1][1] == N
         assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
-        assert cuts[0][1] - cuts[0][0] == max(N // w - relief, 1)
-        rest = [b - a for a, b in cuts[1:]]
+        rr_eff = min(rr, w - 1)
+        assert all(b - a == max(N // w - relief, 1) for a, b in cuts[:rr_eff])
+        rest = [b - a for a, b in cuts[rr_eff:]]
         assert max(rest) - min(rest) <= 1
     assert slab.default_relief(256, 8) == 2 and slab.default_relief(256, 2) == 1 and slab.default_relief(32, 8) == 0
+    assert slab.default_relief(256, 8, spread=True) == 1
 
 
 @pytest.mark.parametrize("world,spread", [(2, False), (3, False), (2, True)])

@@ -10,10 +10,11 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from alignsdf_b200 import slab, synthetic  # noqa: E402
+from alignsdf_b200 import engine, slab, synthetic  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+mode = sys.argv[3] if len(sys.argv) > 3 else "e2e"        # e2e: the public call (files written); dev: reconstruct_slab only
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -23,14 +24,21 @@ hs = [s.to(dev) for s in synthetic.make_batch(S)]
 tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
 
 
+bounds = [engine.get_engine(dec, dev).bind(s.latent, s.specs, s.mano_results, s.obj_results) for s in hs]
+
+
 def run(n):
     for i in range(n):
         s = hs[i % S]
+        if mode == "dev":
+            slab.reconstruct_slab(slab.gpu_backend(bounds[i % S], N, spread=True), N, rank, world, spread=True)
+            continue
         slab.create_mesh_combined_decoder_slab(True, True, False, dec, s.latent, s.mano_results, s.obj_results, None,
                                                s.specs, os.path.join(tmp, f"r{rank}_{i % 2}"), N=N, spread=True)
     dist.barrier(); torch.cuda.synchronize()
 
 
+run(S)
 run(3)
 t0 = time.perf_counter()
 run(S)
@@ -58,7 +66,7 @@ for a, b, name in k:
     tot[name[:56]] = tot.get(name[:56], 0.0) + (b - a)
 lines = [f"rank {rank}: {wall * 1e3:.2f} ms per sample un-profiled; GPU span {(t_end - t_begin) / 1e3 / S:.2f} ms / sample, "
          f"busy {busy / 1e3 / S:.2f}, idle {(t_end - t_begin - busy) / 1e3 / S:.2f} ({len(gaps)} gaps)"]
-for g, at, name in sorted(gaps, reverse=True)[:12]:
+for g, at, name in sorted(gaps, reverse=True)[:int(os.environ.get("TRACE_GAPS", "12"))]:
     lines.append(f"   idle {g / 1e3:7.3f} ms at +{at / 1e3:8.2f} ms, ended by {name[:60]}")
 for name, t in sorted(tot.items(), key=lambda x: -x[1])[:8]:
     lines.append(f"   {t / 1e3 / S:8.3f} ms/sample  {name}")
