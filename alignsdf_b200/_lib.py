@@ -14,8 +14,8 @@ import torch
 ASDF_MAX_LAYERS = 8
 ASDF_MAX_POINT_DIM = 64
 QUERY_GRID_REFERENCE, QUERY_GRID_REGULAR, QUERY_POINTS = 0, 1, 2
-TC_F16X3, TC_F16_F8 = 0, 1          # asdf_tc_launch.kind
-ABI_VERSION = 3
+TC_F16X3, TC_F16_F8, TC_F16X1 = 0, 1, 2          # asdf_tc_launch.kind
+ABI_VERSION = 4
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalignsdf_b200.so")
 
@@ -48,7 +48,9 @@ class TcLaunch(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_decoders", C.c_int32), ("n_samples", C.c_int32), ("reserved", C.c_int32),
                 ("static_dev", C.c_void_p), ("samples_dev", C.c_void_p), ("sample_stride", C.c_int64),
                 ("grid_dev", C.c_void_p), ("out_hand_dev", C.c_void_p), ("out_obj_dev", C.c_void_p),
-                ("out_stride", C.c_int64), ("bbox_dev", C.c_void_p), ("status_dev", C.c_void_p)]
+                ("out_stride", C.c_int64), ("bbox_dev", C.c_void_p), ("status_dev", C.c_void_p),
+                ("bbox_tau", C.c_float), ("amb_capacity", C.c_int32), ("amb_dev", C.c_void_p),
+                ("amb_count_dev", C.c_void_p)]
 
 
 class TcBindDesc(C.Structure):

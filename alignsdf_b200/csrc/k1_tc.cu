@@ -226,6 +226,11 @@ struct Args {
   uint32_t tiles_per_sample;       // 256-point items per sample
   int32_t items_base, items_rem;   // items per CTA pair: items_base (+1 for the first items_rem pairs)
   int32_t n_dec;           // 2: two MLPs (hand, obj) per item; 1: one MLP with two outputs
+  int32_t main_only;       // ASDF_TC_F16X1: the fp16 main product alone (F16_F8 stream, correction tiles skipped)
+  float tau;               // bounding boxes count val < -tau; |val| <= tau goes to the ambiguous list (amb != NULL)
+  float4* amb;             // NULL or [sample][amb_cap] = (x, y, z, bits: grid index | output << 30)
+  int32_t* amb_count;      // [sample] entries wanted so far (may exceed amb_cap: the host then repeats the pass exactly)
+  int32_t amb_cap;
   long long* dbg;          // optional int64[512] of cycle counters of CTA pair 0 (tools/tc_phase_timing.py)
   int dbg_flags;           // debug build only (results become garbage): 1 = no ALO stores, 2 = no weight copies,
                            // 4 = no correction UMMAs, 8 = no fp16 main UMMAs, 16 = no epilogue math (64: layer 0 only)
@@ -331,7 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
           }
           for (int j = 0; j < n; ++j) {                                               // main phase / (hi, correction) pairs
             if (kCorrFirst) { push(mt); mt += kTileBytes; }
-            else { push(mt, 2 * kTileBytes); mt += 2 * kTileBytes; }                  // (hi, correction) pair in one copy
+            else { push(mt, a.main_only ? kTileBytes : 2 * kTileBytes); mt += 2 * kTileBytes; }   // (hi, correction) pair in one copy
             if (g == kPTilesPerDecoder - 1 && has_next) {
               if (j == 2) push(ptile(smp_next, dec_next, 0));
               if (j == 5) push(ptile(smp_next, dec_next, 1));
@@ -360,6 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       // The whole warp walks the schedule (all values warp-uniform -> uniform registers); elect.sync inside the
       // wrappers picks the issuing lane.
       const uint32_t issue = 1u;
+      const bool main_only = a.main_only != 0;       // warp-uniform
       uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
       // uses so far of accumulator buffer X / Y -- scalars, not an indexed array: an array goes to local memory
       // and its (per-thread) loads make the wait loops, and then every descriptor, look divergent to ptxas
@@ -463,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 if (!(kDebug && (a.dbg_flags & 8))) umma_ts_lo(issue, d_tmem, ahi + ks * 8, bh + ks * 2, 1u);
-                if (!(kDebug && (a.dbg_flags & 4))) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b8 + ks * 2, 1u);
+                if (!(kDebug && (a.dbg_flags & 4)) && !main_only) umma_ss8_lo(issue, d_tmem, alo + ks * 2, b8 + ks * 2, 1u);
               }
               release();
               overlap_next(j);
@@ -756,8 +762,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         const float val = tanhf(lds_f1(rbase) + lds_f1(rbase + 4 * kRows) + b4);
         float* out = o == 0 ? a.out_hand : a.out_obj;
         if (it.live && out) out[(int64_t)it.smp * a.out_stride + (it.i - a.q.begin)] = val;
-        if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> o & 1))
-          bbox_update(a.bbox + 12 * it.smp + 6 * o, it.live && val < 0.f, it.i, a.q.N);
+        if (a.bbox && a.q.mode != ASDF_QUERY_POINTS && (a.q.bbox_mask >> o & 1)) {
+          // fast bounding-box pass: only values that are negative whatever this kind's error count; the points it
+          // cannot decide (|val| <= tau, or NaN) are listed for an exact re-evaluation
+          const float thr = a.amb ? -a.tau : 0.f;
+          bbox_update(a.bbox + 12 * it.smp + 6 * o, it.live && val < thr, it.i, a.q.N);
+          if (a.amb && it.live && !(fabsf(val) > a.tau)) {
+            const int slot = atomicAdd(a.amb_count + it.smp, 1);
+            if (slot < a.amb_cap) {
+              float vx = a.q.voxel, o0 = a.q.origin[0], o1 = a.q.origin[1], o2 = a.q.origin[2];
+              if (a.grid) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(a.grid) + it.smp);
+                vx = g.x; o0 = g.y; o1 = g.z; o2 = g.w;
+              }
+              float x0, x1, x2;
+              grid_point(it.i, a.q.N, a.q.mode, vx, o0, o1, o2, x0, x1, x2);
+              a.amb[(int64_t)it.smp * a.amb_cap + slot] =
+                  make_float4(x0, x1, x2, __int_as_float((int)((uint32_t)it.i | ((uint32_t)o << 30))));
+            }
+          }
+        }
       }
       ASDF_STAMP2(12);
     }
@@ -802,7 +826,12 @@ static int launch(const Args& a, unsigned grid, int smem, cudaStream_t stream) {
 static int tc_eval_impl(const asdf_tc_launch* l, const asdf_query* q, void* stream, void* debug_dev) {
   using namespace asdf;
   ASDF_REQUIRE(l && q, "asdf_tc_eval: null argument");
-  ASDF_REQUIRE(l->kind == ASDF_TC_F16X3 || l->kind == ASDF_TC_F16_F8, "asdf_tc_eval: unknown kind");
+  ASDF_REQUIRE(l->kind == ASDF_TC_F16X3 || l->kind == ASDF_TC_F16_F8 || l->kind == ASDF_TC_F16X1, "asdf_tc_eval: unknown kind");
+  ASDF_REQUIRE(!l->amb_dev || (l->amb_count_dev && l->amb_capacity >= 1 && l->bbox_dev && q->mode != ASDF_QUERY_POINTS &&
+                               (int64_t)q->N * q->N * q->N <= ((int64_t)1 << 30) && ((uintptr_t)l->amb_dev & 15) == 0),
+               "asdf_tc_eval: the ambiguous-point list needs a bounding-box grid pass (N^3 <= 2^30), a counter and capacity");
+  ASDF_REQUIRE(l->kind != ASDF_TC_F16X1 || !l->bbox_dev || l->amb_dev,
+               "asdf_tc_eval: bounding boxes of kind ASDF_TC_F16X1 need the ambiguous-point list");
   ASDF_REQUIRE(l->n_decoders == 1 || l->n_decoders == 2, "asdf_tc_eval: n_decoders must be 1 or 2");
   ASDF_REQUIRE(l->static_dev && l->samples_dev && l->status_dev, "asdf_tc_eval: null device pointer");
   ASDF_REQUIRE(l->n_samples >= 1 && (l->n_samples == 1 || l->sample_stride >= tc::kSampleBytes), "asdf_tc_eval: bad sample batch");
@@ -836,20 +865,22 @@ static int tc_eval_impl(const asdf_tc_launch* l, const asdf_query* q, void* stre
   a.tiles_per_sample = (uint32_t)tiles_per_sample;
   a.items_base = (int32_t)(n_tiles / clusters); a.items_rem = (int32_t)(n_tiles % clusters);
   a.n_dec = l->n_decoders;
+  a.main_only = l->kind == ASDF_TC_F16X1;
+  a.tau = l->bbox_tau; a.amb = (float4*)l->amb_dev; a.amb_count = l->amb_count_dev; a.amb_cap = l->amb_capacity;
   a.dbg = (long long*)debug_dev; a.dbg_flags = 0;
   const unsigned grid = (unsigned)(2 * clusters);
 #ifdef ASDF_TC_DEBUG
   if (debug_dev) {
     const char* e = getenv("ASDF_TC_DEBUG_FLAGS");
     a.dbg_flags = e ? atoi(e) : 0;
-    return l->kind == ASDF_TC_F16_F8 ? tc::launch<true, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream)
-                                     : tc::launch<false, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream);
+    return l->kind != ASDF_TC_F16X3 ? tc::launch<true, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream)
+                                    : tc::launch<false, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream);
   }
 #else
   ASDF_REQUIRE(!debug_dev, "asdf_tc_eval_debug: this library was built without ASDF_TC_DEBUG");
 #endif
-  return l->kind == ASDF_TC_F16_F8 ? tc::launch<true, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream)
-                                   : tc::launch<false, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream);
+  return l->kind != ASDF_TC_F16X3 ? tc::launch<true, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream)
+                                  : tc::launch<false, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream);
 }
 
 extern "C" int asdf_tc_eval(const asdf_tc_launch* l, const asdf_query* q, void* stream) {

@@ -18,8 +18,8 @@ from . import _lib, packer
 from ._lib import AsdfError
 
 INT_MAX = 2 ** 31 - 1
-F16X3, F16_F8 = _lib.TC_F16X3, _lib.TC_F16_F8
-KIND_NAMES = {F16X3: "f16x3", F16_F8: "f16+2xe4m3"}
+F16X3, F16_F8, F16X1 = _lib.TC_F16X3, _lib.TC_F16_F8, _lib.TC_F16X1
+KIND_NAMES = {F16X3: "f16x3", F16_F8: "f16+2xe4m3", F16X1: "f16x1"}
 # ALIGNSDF_B200_PATH: "auto" (default), "f16" (k1_tc F16X3), "f8" (k1_tc F16_F8, no calibration), "simt" (k1_simt)
 _PATH_ALIASES = {"tc2": "f16", "tc3": "f8", "tc": "f16"}
 # "auto" on the shipped topology picks, PER SAMPLE, the fastest kernel that is provably inside the 1e-5 contract:
@@ -41,7 +41,17 @@ CALIB_POINTS = 4096
 CALIB_TOL = 4e-6
 CALIB_FULL_FIRST = 4         # batches of a decoder calibrated against the fp32 kernel unconditionally ...
 CALIB_FULL_EVERY = 16        # ... and every n-th one after them (BoundSample._calibrate)
-STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0, "simt_launches": 0}
+# Pass 1 only feeds the bounding box (utils/mesh.py:46-80), so it runs on the single-product kind F16X1 (half the
+# tensor time of F16_F8) with a sign threshold tau: values below -tau are inside whatever that kind's error, the
+# points within +-tau (a few % of the grid: a shell around the surface) are re-evaluated by the exact kind and merged.
+# tau = FAST_TAU_FACTOR x the largest |F16X1 - fp32| the calibration runs of this decoder have measured; a sample
+# whose own calibration error exceeds tau / FAST_TAU_MARGIN repeats its pass 1 on the exact kind.
+FAST_BBOX = os.environ.get("ALIGNSDF_B200_FAST_BBOX", "1") != "0"
+FAST_TAU_FACTOR = 4.0
+FAST_TAU_MARGIN = 2.0
+FAST_AMB_FRACTION = 8        # ambiguous-list capacity: N^3 / this many entries per sample (16 B each)
+STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0, "simt_launches": 0,
+         "f1_launches": 0, "fast_bbox_passes": 0, "fast_bbox_redone": 0, "fast_bbox_ambiguous": 0}
 FALLBACKS = STATS                # old name
 LAUNCHES = {"count": 0}          # kernels of libalignsdf_b200.so launched so far (bench.py reports it)
 KERNEL_EVENTS = None             # bench.py: a list -> every asdf_tc_eval is bracketed by CUDA events on its stream
@@ -104,7 +114,9 @@ class BoundSample:
         self._latents_host = {}                 # sample index -> latent on the host
         self._tc_inputs = None
         self._tc_blocks = {}                    # kind -> (blocks, p_absmax, bind status)
-        self._calib = None                      # device f32[2]: max |F16_F8 - fp32|, max |F16X3 - fp32| on the calibration points
+        self._calib = None                      # device f32[3]: error bounds of F16_F8, F16X3, F16X1 on the calibration points
+        self._fast_tau = None                   # threshold of the fast bounding-box pass launched for this batch, if any
+        self.redo_fast = False                  # decide(): that pass is void (tau too small for this sample)
         self._calib_checked = False
         self.calib_err = None                   # the same on the host, once verify() has read it
         self._level_floor = LEVEL_F8            # lowest level verify() has cleared for this batch so far
@@ -232,19 +244,28 @@ class BoundSample:
         self._tc_blocks[kind] = (blocks, need, status)
         return blocks, status
 
-    def launch_tc(self, kind, q, n, store=True, box=None, grid=None, p_absmax=2.0, level=None):
-        """One asdf_tc_eval over all S samples (asynchronous, no host sync).
+    def launch_tc(self, kind, q, n, store=True, box=None, grid=None, p_absmax=2.0, level=None, sample=None,
+                  tau=0.0, amb=None, amb_count=None):
+        """One asdf_tc_eval over all S samples, or over sample ``sample`` alone (asynchronous, no host sync).
+        ``amb`` / ``amb_count`` / ``tau``: ambiguous-point list of a bounding-box pass (asdf_tc_launch).
         -> (hand [S,n] | None, obj [S,n] | None, status int32[1]: bit 0 range flag, bit 1 bind failure)."""
         eng, dev = self.engine, self.device
-        blocks, bind_status = self.tc_blocks(kind, p_absmax)
+        data_kind = F16_F8 if kind == F16X1 else kind            # F16X1 reads the F16_F8 streams, corrections skipped
+        blocks, bind_status = self.tc_blocks(data_kind, p_absmax)
+        S = self.S if sample is None else 1
+        if sample is not None:
+            blocks = blocks[sample:sample + 1]
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._pending.append((LEVEL_F8 if kind == F16_F8 else LEVEL_F16, status, bind_status))
-        hand = torch.empty((self.S, n), dtype=torch.float32, device=dev) if store else None
-        obj = torch.empty((self.S, n), dtype=torch.float32, device=dev) if store else None
+        self._pending.append((LEVEL_F16 if kind == F16X3 else LEVEL_F8, status, bind_status))
+        hand = torch.empty((S, n), dtype=torch.float32, device=dev) if store else None
+        obj = torch.empty((S, n), dtype=torch.float32, device=dev) if store else None
         l = _lib.TcLaunch()
-        l.kind, l.n_decoders, l.n_samples = kind, eng.n_dec, self.S
-        l.static_dev = eng.tc_static(kind).data_ptr()
+        l.kind, l.n_decoders, l.n_samples = kind, eng.n_dec, S
+        l.static_dev = eng.tc_static(data_kind).data_ptr()
         l.samples_dev, l.sample_stride = blocks.data_ptr(), blocks.shape[1]
+        if amb is not None:
+            l.bbox_tau, l.amb_capacity = float(tau), int(amb.shape[1])
+            l.amb_dev, l.amb_count_dev = amb.data_ptr(), amb_count.data_ptr()
         l.grid_dev = None if grid is None else grid.data_ptr()
         l.out_hand_dev = None if hand is None else hand.data_ptr()
         l.out_obj_dev = None if obj is None else obj.data_ptr()
@@ -258,17 +279,17 @@ class BoundSample:
             rc = _lib.lib().asdf_tc_eval(C.byref(l), C.byref(q), _lib.stream_ptr(dev))
             if KERNEL_EVENTS is not None:
                 e1.record()
-                KERNEL_EVENTS.append((KIND_NAMES[kind], self.S * n, e0, e1))
+                KERNEL_EVENTS.append((KIND_NAMES[kind], S * n, e0, e1))
         _lib.check(rc, "asdf_tc_eval")
         LAUNCHES["count"] += 1
-        STATS["f8_launches" if kind == F16_F8 else "f16_launches"] += 1
+        STATS[{F16_F8: "f8_launches", F16X3: "f16_launches", F16X1: "f1_launches"}[kind]] += 1
         self.kinds_used.add(KIND_NAMES[kind])
         return hand, obj, status
 
     def _calibrate(self):
         """Launch (once per bound batch, asynchronously) the calibration comparison on the decoder's fixed random
-        points -> device f32[2] = bound on max |F16_F8 - fp32|, on max |F16X3 - fp32| (inf for a kind no longer in
-        play).
+        points -> device f32[3] = bound on max |F16_F8 - fp32|, on max |F16X3 - fp32|, on max |F16X1 - fp32| (inf for a
+        kind not in play).
 
         FULL: the exact-fp32 kernel against both tensor-core kinds -- the first CALIB_FULL_FIRST batches of a decoder
         and every CALIB_FULL_EVERY-th after them.  LIGHT (all other batches): F16_F8 against F16X3 only, and
@@ -287,24 +308,32 @@ class BoundSample:
             full = bound16 is None or k < CALIB_FULL_FIRST or (k - CALIB_FULL_FIRST) % CALIB_FULL_EVERY == 0
             self._calib_full = full
             errs = []
+            inf = torch.full((), float("inf"), device=self.device)
+            fast = FAST_BBOX and eng.level < LEVEL_SIMT
             if full:
                 ref = [self._launch_simt(q, n, False, None, i)[:2] for i in range(self.S)]
                 rh, ro = torch.stack([r[0] for r in ref]), torch.stack([r[1] for r in ref])
                 for lvl in (LEVEL_F8, LEVEL_F16):
                     if lvl < eng.level:
-                        errs.append(torch.full((), float("inf"), device=self.device))
+                        errs.append(inf)
                         continue
                     h, o, _ = self.launch_tc(LEVEL_KIND[lvl], q, n, level=lvl)
                     errs.append(torch.maximum((h - rh).abs().max(), (o - ro).abs().max()))
+                e16 = 0.0
             else:
                 e16 = torch.full((), float(bound16), device=self.device)
+                rh, ro, _ = self.launch_tc(F16X3, q, n, level=LEVEL_F16)
                 if eng.level <= LEVEL_F8:
-                    h16, o16, _ = self.launch_tc(F16X3, q, n, level=LEVEL_F16)
                     h8, o8, _ = self.launch_tc(F16_F8, q, n, level=LEVEL_F8)
-                    errs.append(torch.maximum((h8 - h16).abs().max(), (o8 - o16).abs().max()) + e16)
+                    errs.append(torch.maximum((h8 - rh).abs().max(), (o8 - ro).abs().max()) + e16)
                 else:
-                    errs.append(torch.full((), float("inf"), device=self.device))
+                    errs.append(inf)
                 errs.append(e16)
+            if fast:                                # the single-product kind of the bounding-box pass
+                h1, o1, _ = self.launch_tc(F16X1, q, n, level=LEVEL_F8)
+                errs.append(torch.maximum((h1 - rh).abs().max(), (o1 - ro).abs().max()) + e16)
+            else:
+                errs.append(inf)
             self._calib = torch.stack(errs)
         return self._calib
 
@@ -323,9 +352,9 @@ class BoundSample:
         return lvl if self.tc_ok else LEVEL_SIMT
 
     def pending_flags(self):
-        """Device int32[4] describing everything launched since the last call, without waiting for it:
-        [OR of the status | bind words of the F16_F8 launches, the same for the F16X3 launches, bit pattern of the
-        calibration error of F16_F8, of F16X3 (0 = no calibration result pending)].  Words of several ranks
+        """Device int32[5] describing everything launched since the last call, without waiting for it:
+        [OR of the status | bind words of the F16_F8 / F16X1 launches, the same for the F16X3 launches, bit patterns
+        of the calibration error bounds of F16_F8, F16X3, F16X1 (0 = no calibration result pending)].  Words of several ranks
         combine with an elementwise MAX (positive floats order like their bit patterns)."""
         pending, self._pending = self._pending, []
         dev = self.device
@@ -341,18 +370,23 @@ class BoundSample:
             self._calib.record_stream(cur)
             cal = self._calib.to(torch.float32).view(torch.int32)
         else:
-            cal = torch.zeros(2, dtype=torch.int32, device=dev)
+            cal = torch.zeros(3, dtype=torch.int32, device=dev)
         return torch.cat([torch.stack(words), cal])
 
     def decide(self, flags):
         """Host half of the check: ``flags`` = the four ints of pending_flags() (of this process, or the MAX over the
         ranks of a slab group -- every rank then takes the same decision).  -> the lowest level whose results can
         be trusted for this batch; launches made below it must be repeated at that level."""
-        w8, w16, b8, b16 = (int(x) for x in flags)
+        w8, w16, b8, b16, b1 = (int(x) for x in flags)
         eng = self.engine
         need = self._level_floor
-        if b8 or b16:
-            e8, e16 = (float(np.array([b], np.int32).view(np.float32)[0]) for b in (b8, b16))
+        if b8 or b16 or b1:
+            e8, e16, e1 = (float(np.array([b], np.int32).view(np.float32)[0]) for b in (b8, b16, b1))
+            if np.isfinite(e1):
+                # a bounding-box pass launched with a threshold this sample's own error does not respect is void
+                if self._fast_tau is not None and not e1 * FAST_TAU_MARGIN <= self._fast_tau:
+                    self.redo_fast = True
+                eng.calib["f1"] = max(e1, eng.calib.get("f1") or 0.0)
             if not self._calib_checked:
                 self._calib_checked = True
                 eng.calib["samples"] += self.S
@@ -447,11 +481,53 @@ class BoundSample:
         hand, obj, cls, _ = self._run(q, pts.shape[0], want_cls, False, pth, pmax, want_logits)
         return hand, obj, cls
 
+    # ------------------------------------------------------------------ pass 1 on the single-product kind
+    def fast_bbox_pass(self, kind, q, n, box, tau, calibrate=False, grid=None):
+        """Bounding boxes of the grid query ``q`` (all S samples) into ``box`` [S,12] through the single-product
+        kind: F16X1 launch with threshold ``tau`` and an ambiguous-point list, then the listed points (|val| <= tau:
+        a shell around the surface) through the exact kind ``kind`` and their signs merged into the boxes.  The
+        result equals ``launch_tc(kind, q, ..., box)`` as long as tau bounds F16X1's error (decide() checks this
+        sample's own calibration against it and sets ``redo_fast`` otherwise).  Waits once for the GPU (the list
+        sizes); an overflowing list falls back to the exact pass."""
+        dev, S, N = self.device, self.S, int(q.N)
+        cap = max(n // FAST_AMB_FRACTION, 1 << 14)
+        amb = torch.empty((S, cap, 4), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(S, dtype=torch.int32, device=dev)
+        self._fast_tau = float(tau)
+        self.launch_tc(F16X1, q, n, False, box, grid, tau=tau, amb=amb, amb_count=cnt)
+        if calibrate and self.engine.level < LEVEL_SIMT:
+            self._calibrate()                  # queued behind the pass; its host work overlaps it
+        STATS["fast_bbox_passes"] += 1
+        counts = cnt.cpu().tolist()
+        if max(counts) > cap:                  # the shell does not fit: this decoder's tau is too coarse for the grid
+            STATS["fast_bbox_redone"] += 1
+            box.copy_(new_bbox(dev, S))
+            self.launch_tc(kind, q, n, False, box, grid)
+            return
+        nn_ = N * N
+        for s_i, c in enumerate(counts):
+            if c == 0:
+                continue
+            STATS["fast_bbox_ambiguous"] += c
+            pts = amb[s_i, :c]
+            h, o, _ = self.launch_tc(kind, make_query(_lib.QUERY_POINTS, end=c, points=pts), c, True, sample=s_i)
+            w = pts[:, 3].contiguous().view(torch.int32)
+            idx, which = (w & 0x3FFFFFFF).long(), (w >> 30) & 1
+            ijk = torch.stack([idx // nn_, (idx // N) % N, idx % N], 1).to(torch.int32)
+            for b in range(2):
+                neg = (which == b) & ((h[0] if b == 0 else o[0]) < 0)
+                big = torch.full_like(ijk, INT_MAX)
+                lo = torch.where(neg[:, None], ijk, big).amin(0)
+                hi = torch.where(neg[:, None], ijk, -torch.ones_like(ijk)).amax(0)
+                box[s_i, 6 * b:6 * b + 3] = torch.minimum(box[s_i, 6 * b:6 * b + 3], lo)
+                box[s_i, 6 * b + 3:6 * b + 6] = torch.maximum(box[s_i, 6 * b + 3:6 * b + 6], hi)
+
     # ------------------------------------------------------------------ the two grid passes of a batch, no host sync
     def two_pass(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False, calibrate=None):
         """utils/mesh.py:24-120 for all S samples: pass 1 over [-1,1]^3 (bounding boxes only unless
         ``keep_pass1``), asdf_regrid on the device, pass 2 on the per-sample lattices.  Nothing here waits for
-        the GPU; call verify() once the results are needed.
+        the GPU -- except the fast bounding-box pass (fast_bbox_pass reads its list sizes between the passes) --;
+        call verify() once the results are needed.
         -> dict(hand [S,N^3], obj [S,N^3], grid [S,4] = voxel, origin, minmax [S,6], box [S,12], pass1_*)."""
         dev = self.device
         level = self.auto_level() if level is None else level
@@ -462,9 +538,15 @@ class BoundSample:
         voxel = 2.0 / (N - 1)
         q1 = make_query(_GRID_MODES[mode], N, 0, n, voxel, (-1.0, -1.0, -1.0), bbox_mask=bbox_mask)
         box = new_bbox(dev, self.S)
-        p1h, p1o, _ = self.launch_tc(kind, q1, n, keep_pass1, box)
-        if (self.engine.path == "auto" if calibrate is None else calibrate) and self.engine.level < LEVEL_SIMT:
-            self._calibrate()               # (once per batch) queued behind pass 1; its host work overlaps the pass
+        auto = self.engine.path == "auto" if calibrate is None else calibrate
+        tau = self.engine.fast_tau() if (auto and not keep_pass1 and not self.redo_fast) else None
+        if tau is not None:
+            p1h = p1o = None
+            self.fast_bbox_pass(kind, q1, n, box, tau, calibrate=True)
+        else:
+            p1h, p1o, _ = self.launch_tc(kind, q1, n, keep_pass1, box)
+            if auto and self.engine.level < LEVEL_SIMT:
+                self._calibrate()           # (once per batch) queued behind pass 1; its host work overlaps the pass
         grid = torch.empty((self.S, 4), dtype=torch.float32, device=dev)
         minmax = torch.empty((self.S, 6), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -473,7 +555,8 @@ class BoundSample:
         LAUNCHES["count"] += 1
         q2 = make_query(_GRID_MODES[mode], N, 0, n, 0.0, (0.0, 0.0, 0.0))
         hand, obj, _ = self.launch_tc(kind, q2, n, True, None, grid)
-        return dict(hand=hand, obj=obj, grid=grid, minmax=minmax, box=box, pass1_hand=p1h, pass1_obj=p1o, level=level)
+        return dict(hand=hand, obj=obj, grid=grid, minmax=minmax, box=box, pass1_hand=p1h, pass1_obj=p1o, level=level,
+                    fast_bbox=tau is not None)
 
     def _two_pass_simt(self, N, bbox_mask, mode, keep_pass1):
         """The same two passes on the exact-fp32 generic kernel, sample after sample (level 2: decoders neither
@@ -525,8 +608,16 @@ class DecoderEngine:
         self._bind_static = None
         self._calib_points = None
         self.level = LEVEL_F8 if self.tc_supported else LEVEL_SIMT     # raised (for good) when a calibration rejects a kind
-        self.calib = dict(f8=None, f16=None, tol=CALIB_TOL, points=CALIB_POINTS, samples=0, samples_full=0,
+        self.calib = dict(f8=None, f16=None, f1=None, tol=CALIB_TOL, points=CALIB_POINTS, samples=0, samples_full=0,
                           launched=0)   # worst error bounds seen; batches calibrated (against the fp32 kernel)
+
+    def fast_tau(self):
+        """Sign threshold for a bounding-box pass on the single-product kind, or None while this decoder has no
+        measured error bound for it yet (its first sample runs pass 1 on the exact kind)."""
+        e1 = self.calib.get("f1")
+        if not FAST_BBOX or e1 is None or not np.isfinite(e1) or self.level >= LEVEL_SIMT:
+            return None
+        return FAST_TAU_FACTOR * max(e1, 1e-7)
 
     def tc_static(self, kind):
         """Packed weight stream of `kind`, resident in HBM (built on first use)."""

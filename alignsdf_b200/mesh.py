@@ -173,10 +173,10 @@ def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None, launche
         if r is None:
             r = bound.two_pass(N, mask, grid_mode, lvl, keep_pass1, calibrate=auto)
         need = bound.verify()
-        if need <= lvl:
+        if need <= lvl and not (bound.redo_fast and r.get("fast_bbox")):
             bound.last_kind = _engine.LEVEL_NAMES[lvl]
             return r
-        lvl, r = need, None
+        lvl, r = max(need, lvl), None          # rejected kind, or a fast bounding-box pass whose threshold was too small
 
 
 def _volumes_from_two_pass(r, bound, N):
@@ -351,10 +351,10 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
                 with torch.cuda.stream(side[dev]):
                     side[dev].wait_event(done)
                     host = small.cpu().tolist()
-                need = bound.decide([int(x) for x in host[:4]])
-                if need <= lvl:
+                need = bound.decide([int(x) for x in host[:5]])
+                if need <= lvl and not (bound.redo_fast and r.get("fast_bbox")):
                     bound.last_kind = _engine.LEVEL_NAMES[lvl]
-                    g, mm = torch.tensor(host[4:8], dtype=torch.float32), torch.tensor(host[8:14], dtype=torch.float32)
+                    g, mm = torch.tensor(host[5:9], dtype=torch.float32), torch.tensor(host[9:15], dtype=torch.float32)
                     view = lambda t: t[0].view(N, N, N)
                     vols = dict(hand=view(r["hand"]), obj=view(r["obj"]), voxel=g[0].clone(), origin=g[1:4].clone(),
                                 min_index=mm[:3].clone(), max_index=mm[3:].clone(), bound=bound)

@@ -4,7 +4,7 @@ The reference only has sample-level parallelism (dist_reconstruct.py:63-84: one 
 GPU, no communication).  This module adds the north star's second mode: grid axis 0 is cut into
 ``world`` contiguous slabs, one process per GPU (torchrun / torch.distributed):
 
-  pass 1   each rank evaluates its slab and reduces a local bbox   -> ONE all_reduce(MIN) of 16 ints
+  pass 1   each rank evaluates its slab and reduces a local bbox   -> ONE all_reduce(MIN) of 17 ints
                                                                       (bbox + the kernel's range / calibration flags)
   re-grid  identical arithmetic on every rank, on the device        (utils/mesh.py:249-254, asdf_regrid)
   pass 2   each rank evaluates its slab of the refit grid
@@ -31,7 +31,7 @@ import torch.distributed as dist
 
 INT_MAX = 2 ** 31 - 1
 INT64_MAX = 2 ** 63 - 1
-N_FLAGS = 4                    # engine.BoundSample.pending_flags()
+N_FLAGS = 5                    # engine.BoundSample.pending_flags()
 
 
 def slab_planes(N: int, rank: int, world: int, relief: int = 0, relief_ranks: int = 1):
@@ -300,13 +300,18 @@ def gpu_backend(bound, N, grid_mode="reference", path=None, spread=False) -> Bac
     def pass1(begin, end, mask):
         state["level"] = lvl = bound.auto_level(path, calibrate=False)
         box = engine.new_bbox(dev)
+        auto = not forced and bound.tc_ok and lvl < engine.LEVEL_SIMT
+        tau = bound.engine.fast_tau() if (auto and not bound.redo_fast) else None
+        state["fast"] = tau is not None and end > begin
         if end > begin:
             q = engine.make_query(mode, N, begin, end, vs1, (-1.0, -1.0, -1.0), bbox_mask=mask)
             if lvl >= engine.LEVEL_SIMT:
                 bound._launch_simt(q, end - begin, False, box[0])
+            elif tau is not None:           # single-product kind + exact re-evaluation of the shell around the surface
+                bound.fast_bbox_pass(engine.LEVEL_KIND[lvl], q, end - begin, box, tau, calibrate=True)
             else:
                 bound.launch_tc(engine.LEVEL_KIND[lvl], q, end - begin, False, box)
-        if not forced and bound.tc_ok and lvl < engine.LEVEL_SIMT:
+        if auto:
             bound._calibrate()              # (once per sample) queued behind pass 1: its host work overlaps the pass
         return box[0], bound.pending_flags()
 
@@ -343,7 +348,9 @@ def gpu_backend(bound, N, grid_mode="reference", path=None, spread=False) -> Bac
 
     def decide(flags):
         need = bound.decide(flags)
-        return need > state["level"] and not forced           # a forced kind cannot be replaced: keep its results
+        if forced:                                             # a forced kind cannot be replaced: keep its results
+            return False
+        return need > state["level"] or (bound.redo_fast and state.get("fast", False))
 
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     return Backend(pass1, regrid, pass2, mc_count, mc_emit, dev, default_relief(N, world, spread), decide,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ASDF_ABI_VERSION 3
+#define ASDF_ABI_VERSION 4
 #define ASDF_MAX_LAYERS 8
 #define ASDF_MAX_POINT_DIM 64
 
@@ -121,6 +121,14 @@ int asdf_simt_eval(const asdf_simt_desc* desc, const float* static_dev, const fl
  *   through the next safer kernel (F16_F8 -> F16X3 -> asdf_simt_eval). */
 #define ASDF_TC_F16X3 0
 #define ASDF_TC_F16_F8 1
+/* Bounding-box-only kind for pass 1 (the reference uses that pass for nothing but the box, utils/mesh.py:46-80): the
+ * fp16 main product ALONE (static / sample blocks of kind ASDF_TC_F16_F8; half its tensor time).  Its error (~1e-4 x
+ * output range) cannot decide the sign of values near zero, so the launch takes a threshold: points with
+ * val < -bbox_tau enter the box, points with |val| <= bbox_tau are appended to amb_dev -- (x, y, z, bits = grid index |
+ * output << 30) per entry, amb_count_dev[sample] counts the entries WANTED -- and the caller re-evaluates those
+ * exactly (ASDF_QUERY_POINTS through an exact kind) and merges their signs into the box: the result equals the
+ * exact kind's box whenever bbox_tau bounds this kind's error (the caller calibrates it per sample). */
+#define ASDF_TC_F16X1 2
 typedef struct {
   int32_t kind;
   int32_t n_decoders;
@@ -135,6 +143,10 @@ typedef struct {
   int64_t out_stride;
   int32_t* bbox_dev;
   int32_t* status_dev;
+  float bbox_tau;           /* with amb_dev: sign threshold of the bounding boxes (see ASDF_TC_F16X1); any kind */
+  int32_t amb_capacity;     /* entries per sample */
+  void* amb_dev;            /* NULL or float4[n_samples][amb_capacity] */
+  int32_t* amb_count_dev;   /* int32[n_samples], zeroed by the caller */
 } asdf_tc_launch;
 int asdf_tc_eval(const asdf_tc_launch* l, const asdf_query* q, void* stream);
 int64_t asdf_tc_static_bytes(int32_t kind, int32_t n_decoders);

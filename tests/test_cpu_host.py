@@ -166,7 +166,7 @@ def test_shared_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.asdf_abi_version.restype = ctypes.c_int
-    assert lib.asdf_abi_version() == 3
+    assert lib.asdf_abi_version() == 4
 
 
 def test_ctypes_structs_match_header_sizes(tmp_path):

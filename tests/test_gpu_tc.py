@@ -257,3 +257,71 @@ def test_full_512_grid_against_the_fp32_kernel():
         hs, os_, _, _ = bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], begin=a, end=min(a + step, N ** 3), path="simt")
         worst = max(worst, float((ht[a:a + step] - hs).abs().max()), float((ot[a:a + step] - os_).abs().max()))
     assert worst <= TOL, worst
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pass 1 on the single-product kind (bounding boxes only) + exact re-evaluation of the shell around the surface
+# ----------------------------------------------------------------------------------------------------------------
+def _exact_box(bound, N, kind, mask=3, begin=0, end=None):
+    end = N ** 3 if end is None else end
+    q = engine.make_query(_lib.QUERY_GRID_REFERENCE, N, begin, end, 2.0 / (N - 1), (-1.0, -1.0, -1.0), bbox_mask=mask)
+    box = engine.new_bbox(DEV, bound.S)
+    bound.launch_tc(kind, q, end - begin, False, box)
+    return q, box
+
+
+@pytest.mark.parametrize("init,gain,N", [("default", 1.0, 96), ("plain", 4.0, 64), ("engineered", 1.0, 80)])
+def test_fast_bounding_box_pass_equals_the_exact_pass(init, gain, N):
+    dec = synthetic.make_decoder(41, init=init, out_gain=gain)
+    smp = [s.to(DEV) for s in synthetic.make_batch(2, base_seed=41)]
+    eng = engine.get_engine(dec, DEV)
+    bound = eng.bind_batch([(s.latent, s.specs, s.mano_results, s.obj_results) for s in smp])
+    bound._calibrate()
+    assert bound.verify() < engine.LEVEL_SIMT
+    e1 = eng.calib["f1"]
+    assert e1 is not None and 0 < e1 < 5e-3
+    kind = engine.LEVEL_KIND[eng.level]
+    q, want = _exact_box(bound, N, kind)
+    before = dict(engine.STATS)
+    for tau in (eng.fast_tau(), 10 * eng.fast_tau()):                     # a wider shell must give the same boxes
+        box = engine.new_bbox(DEV, bound.S)
+        bound.fast_bbox_pass(kind, q, N ** 3, box, tau)
+        assert torch.equal(box, want), (tau, box.tolist(), want.tolist())
+    assert engine.STATS["fast_bbox_passes"] == before["fast_bbox_passes"] + 2
+    assert engine.STATS["fast_bbox_ambiguous"] > before["fast_bbox_ambiguous"]
+    assert engine.STATS["fast_bbox_redone"] == before["fast_bbox_redone"]
+    # a sub-range of the grid (z-slab) and a single branch
+    q2, want2 = _exact_box(bound, N, kind, mask=2, begin=5 * N * N + 7, end=31 * N * N)
+    box = engine.new_bbox(DEV, bound.S)
+    bound.fast_bbox_pass(kind, q2, 31 * N * N - (5 * N * N + 7), box, eng.fast_tau())
+    assert torch.equal(box, want2)
+    # a threshold so large that the list overflows: the pass falls back to the exact kind
+    box = engine.new_bbox(DEV, bound.S)
+    bound.fast_bbox_pass(kind, q, N ** 3, box, 2.0)
+    assert torch.equal(box, want) and engine.STATS["fast_bbox_redone"] == before["fast_bbox_redone"] + 1
+
+
+def test_fast_bounding_box_threshold_is_checked_per_sample(tmp_path):
+    """The drop-in call uses the fast pass from a decoder's second sample on; a threshold that this sample's own
+    calibration does not support voids the pass (it is repeated exactly) -- the result never depends on it."""
+    N = 64
+    dec = synthetic.make_decoder(43, init="default")
+    smp = [s.to(DEV) for s in synthetic.make_batch(3, base_seed=43)]
+    eng = engine.get_engine(dec, DEV)
+    ref = []
+    try:
+        engine.FAST_BBOX = False
+        dec2 = synthetic.make_decoder(43, init="default")
+        for s in smp:
+            v = amesh.sdf_volumes(dec2, s.latent, s.mano_results, s.obj_results, s.specs, N, keep_pass1=False)
+            ref.append((float(v["voxel"]), v["origin"].clone(), v["hand"].clone()))
+    finally:
+        engine.FAST_BBOX = True
+    before = dict(engine.STATS)
+    for k, s in enumerate(smp):
+        if k == 2:
+            eng.calib["f1"] = eng.calib["f1"] * 1e-3                      # pretend earlier samples were far more benign
+        v = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N, keep_pass1=False)
+        assert float(v["voxel"]) == ref[k][0] and torch.equal(v["origin"], ref[k][1]) and torch.equal(v["hand"], ref[k][2])
+        assert v["bound"].redo_fast == (k == 2)
+    assert engine.STATS["fast_bbox_passes"] == before["fast_bbox_passes"] + 2          # samples 1 and 2 (0 has no bound yet)
