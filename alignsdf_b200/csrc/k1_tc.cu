@@ -591,11 +591,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         }
       }
     };
+    // ASDF_TC_F16X1 (main product only): no correction operands are computed or stored
+    const bool hi_only = a.main_only != 0;
+    auto split32_hi = [&](const float* acc, float inv, uint32_t* hi) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x = fmaxf(acc[2 * i] * inv, 0.f), y = fmaxf(acc[2 * i + 1] * inv, 0.f);
+        const __half2 h = __floats2half2_rn(x, y);
+        vmax2 = __hmax2(vmax2, h);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    };
     // write 32 features [32*h, 32*h+32) of chunk `pos` of this thread's row: hi16 -> TMEM, corrections -> ALO slot
     auto store_half = [&](int pos, int h, const uint32_t* hi, const uint32_t* cr) {
       tmem_st16(tmem_base + lane_addr + kAhiCol + pos * 32 + h * 16, hi);
       const uint32_t base = a_lo + pos * kSlotBytes + (row >> 3) * 1024 + (row & 7) * 128;
       if (kDebug && (a.dbg_flags & 1)) return;
+      if (kF8 && hi_only) return;
       if constexpr (kF8) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -685,7 +697,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
         float acc[32];
         tmem_ld32(acc_addr + h * 32, acc);
         tmem_ld_wait();
-        if (!(kDebug && ((a.dbg_flags & 16) || ((a.dbg_flags & 64) && layer == 0)))) split32(acc, inv, hi[h], cr[h]);
+        if (!(kDebug && ((a.dbg_flags & 16) || ((a.dbg_flags & 64) && layer == 0)))) {
+          if (kF8 && hi_only) split32_hi(acc, inv, hi[h]);
+          else split32(acc, inv, hi[h], cr[h]);
+        }
       }
       free_acc(buf);
       ASDF_STAMP2(8 + layer);

@@ -283,7 +283,7 @@ def test_fast_bounding_box_pass_equals_the_exact_pass(init, gain, N):
     kind = engine.LEVEL_KIND[eng.level]
     q, want = _exact_box(bound, N, kind)
     before = dict(engine.STATS)
-    for tau in (eng.fast_tau(), 10 * eng.fast_tau()):                     # a wider shell must give the same boxes
+    for tau in (eng.fast_tau(), 2 * eng.fast_tau()):                      # a wider shell must give the same boxes
         box = engine.new_bbox(DEV, bound.S)
         bound.fast_bbox_pass(kind, q, N ** 3, box, tau)
         assert torch.equal(box, want), (tau, box.tolist(), want.tolist())
