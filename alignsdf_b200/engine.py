@@ -71,10 +71,21 @@ def _device_of(latent, device=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_BBOX_INIT = {}
+
+
 def new_bbox(device, n=1):
-    """int32[n,12] bounding boxes in their initial state ({INT_MAX x3, -1 x3} per branch)."""
-    return torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3, dtype=torch.int32,
-                        device=device).repeat(n, 1)
+    """int32[n,12] bounding boxes in their initial state ({INT_MAX x3, -1 x3} per branch).  Built from a constant
+    that lives on the device: a host-to-device copy of pageable memory would wait for everything queued on the
+    stream (a whole grid pass, when the next sample is being queued behind the current one)."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    init = _BBOX_INIT.get(device)
+    if init is None:
+        init = _BBOX_INIT[device] = torch.tensor([INT_MAX] * 3 + [-1] * 3 + [INT_MAX] * 3 + [-1] * 3,
+                                                 dtype=torch.int32, device=device)
+    return init.repeat(n, 1)
 
 
 def make_query(mode, N=0, begin=0, end=0, voxel=0.0, origin=(0.0, 0.0, 0.0), points=None, bbox_mask=0):
@@ -482,14 +493,9 @@ class BoundSample:
         return hand, obj, cls
 
     # ------------------------------------------------------------------ pass 1 on the single-product kind
-    def fast_bbox_pass(self, kind, q, n, box, tau, calibrate=False, grid=None):
-        """Bounding boxes of the grid query ``q`` (all S samples) into ``box`` [S,12] through the single-product
-        kind: F16X1 launch with threshold ``tau`` and an ambiguous-point list, then the listed points (|val| <= tau:
-        a shell around the surface) through the exact kind ``kind`` and their signs merged into the boxes.  The
-        result equals ``launch_tc(kind, q, ..., box)`` as long as tau bounds F16X1's error (decide() checks this
-        sample's own calibration against it and sets ``redo_fast`` otherwise).  Waits once for the GPU (the list
-        sizes); an overflowing list falls back to the exact pass."""
-        dev, S, N = self.device, self.S, int(q.N)
+    def fast_bbox_begin(self, kind, q, n, box, tau, calibrate=False, grid=None):
+        """First half of fast_bbox_pass: the F16X1 launch (asynchronous).  -> context for fast_bbox_end."""
+        dev, S = self.device, self.S
         cap = max(n // FAST_AMB_FRACTION, 1 << 14)
         amb = torch.empty((S, cap, 4), dtype=torch.float32, device=dev)
         cnt = torch.zeros(S, dtype=torch.int32, device=dev)
@@ -498,6 +504,12 @@ class BoundSample:
         if calibrate and self.engine.level < LEVEL_SIMT:
             self._calibrate()                  # queued behind the pass; its host work overlaps it
         STATS["fast_bbox_passes"] += 1
+        return (kind, q, n, box, grid, amb, cnt, cap)
+
+    def fast_bbox_end(self, ctx):
+        """Second half: wait for the list sizes, re-evaluate the listed points exactly, merge their signs."""
+        kind, q, n, box, grid, amb, cnt, cap = ctx
+        dev, S, N = self.device, self.S, int(q.N)
         counts = cnt.cpu().tolist()
         if max(counts) > cap:                  # the shell does not fit: this decoder's tau is too coarse for the grid
             STATS["fast_bbox_redone"] += 1
@@ -522,17 +534,24 @@ class BoundSample:
                 box[s_i, 6 * b:6 * b + 3] = torch.minimum(box[s_i, 6 * b:6 * b + 3], lo)
                 box[s_i, 6 * b + 3:6 * b + 6] = torch.maximum(box[s_i, 6 * b + 3:6 * b + 6], hi)
 
-    # ------------------------------------------------------------------ the two grid passes of a batch, no host sync
-    def two_pass(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False, calibrate=None):
-        """utils/mesh.py:24-120 for all S samples: pass 1 over [-1,1]^3 (bounding boxes only unless
-        ``keep_pass1``), asdf_regrid on the device, pass 2 on the per-sample lattices.  Nothing here waits for
-        the GPU -- except the fast bounding-box pass (fast_bbox_pass reads its list sizes between the passes) --;
-        call verify() once the results are needed.
-        -> dict(hand [S,N^3], obj [S,N^3], grid [S,4] = voxel, origin, minmax [S,6], box [S,12], pass1_*)."""
-        dev = self.device
+    def fast_bbox_pass(self, kind, q, n, box, tau, calibrate=False, grid=None):
+        """Bounding boxes of the grid query ``q`` (all S samples) into ``box`` [S,12] through the single-product
+        kind: F16X1 launch with threshold ``tau`` and an ambiguous-point list, then the listed points (|val| <= tau:
+        a shell around the surface) through the exact kind ``kind`` and their signs merged into the boxes.  The
+        result equals ``launch_tc(kind, q, ..., box)`` as long as tau bounds F16X1's error (decide() checks this
+        sample's own calibration against it and sets ``redo_fast`` otherwise).  Waits once for the GPU (the list
+        sizes); an overflowing list falls back to the exact pass."""
+        self.fast_bbox_end(self.fast_bbox_begin(kind, q, n, box, tau, calibrate, grid))
+
+    # ------------------------------------------------------------------ the two grid passes of a batch
+    def two_pass_begin(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False, calibrate=None):
+        """Queue pass 1 of utils/mesh.py:24-120 for all S samples over [-1,1]^3 (bounding boxes only unless
+        ``keep_pass1``; on the single-product kind once the decoder has an error bound for it) and, once per
+        batch, the calibration run behind it.  Nothing here waits for the GPU.  -> context for two_pass_end."""
         level = self.auto_level() if level is None else level
         if level >= LEVEL_SIMT:
-            return self._two_pass_simt(N, bbox_mask, mode, keep_pass1)
+            return dict(simt=(N, bbox_mask, mode, keep_pass1))
+        dev = self.device
         kind = LEVEL_KIND[level]
         n = N ** 3
         voxel = 2.0 / (N - 1)
@@ -540,23 +559,39 @@ class BoundSample:
         box = new_bbox(dev, self.S)
         auto = self.engine.path == "auto" if calibrate is None else calibrate
         tau = self.engine.fast_tau() if (auto and not keep_pass1 and not self.redo_fast) else None
+        fast, p1h, p1o = None, None, None
         if tau is not None:
-            p1h = p1o = None
-            self.fast_bbox_pass(kind, q1, n, box, tau, calibrate=True)
+            fast = self.fast_bbox_begin(kind, q1, n, box, tau, calibrate=True)
         else:
             p1h, p1o, _ = self.launch_tc(kind, q1, n, keep_pass1, box)
             if auto and self.engine.level < LEVEL_SIMT:
                 self._calibrate()           # (once per batch) queued behind pass 1; its host work overlaps the pass
+        return dict(N=N, mask=bbox_mask, mode=mode, level=level, kind=kind, box=box, fast=fast, p1h=p1h, p1o=p1o)
+
+    def two_pass_end(self, ctx):
+        """asdf_regrid on the device and pass 2 on the per-sample lattices.  Waits for the GPU only after a fast
+        bounding-box pass (its list sizes); call verify() once the results are needed.
+        -> dict(hand [S,N^3], obj [S,N^3], grid [S,4] = voxel, origin, minmax [S,6], box [S,12], pass1_*)."""
+        if "simt" in ctx:
+            return self._two_pass_simt(*ctx["simt"])
+        dev, N, box, kind = self.device, ctx["N"], ctx["box"], ctx["kind"]
+        n = N ** 3
+        if ctx["fast"] is not None:
+            self.fast_bbox_end(ctx["fast"])
         grid = torch.empty((self.S, 4), dtype=torch.float32, device=dev)
         minmax = torch.empty((self.S, 6), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().asdf_regrid(_lib.ptr(box), self.S, int(bbox_mask), N, float(np.float32(voxel)),
+            _lib.check(_lib.lib().asdf_regrid(_lib.ptr(box), self.S, int(ctx["mask"]), N, float(np.float32(2.0 / (N - 1))),
                                               _lib.ptr(grid), _lib.ptr(minmax), _lib.stream_ptr(dev)), "asdf_regrid")
         LAUNCHES["count"] += 1
-        q2 = make_query(_GRID_MODES[mode], N, 0, n, 0.0, (0.0, 0.0, 0.0))
+        q2 = make_query(_GRID_MODES[ctx["mode"]], N, 0, n, 0.0, (0.0, 0.0, 0.0))
         hand, obj, _ = self.launch_tc(kind, q2, n, True, None, grid)
-        return dict(hand=hand, obj=obj, grid=grid, minmax=minmax, box=box, pass1_hand=p1h, pass1_obj=p1o, level=level,
-                    fast_bbox=tau is not None)
+        return dict(hand=hand, obj=obj, grid=grid, minmax=minmax, box=box, pass1_hand=ctx["p1h"], pass1_obj=ctx["p1o"],
+                    level=ctx["level"], fast_bbox=ctx["fast"] is not None)
+
+    def two_pass(self, N, bbox_mask, mode="reference", level=None, keep_pass1=False, calibrate=None):
+        """two_pass_begin + two_pass_end."""
+        return self.two_pass_end(self.two_pass_begin(N, bbox_mask, mode, level, keep_pass1, calibrate))
 
     def _two_pass_simt(self, N, bbox_mask, mode, keep_pass1):
         """The same two passes on the exact-fp32 generic kernel, sample after sample (level 2: decoders neither

@@ -379,15 +379,19 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
                 nxt = binder.submit(bind, idx + 1) if idx + 1 < len(samples) else None
                 torch.cuda.current_stream(dev).wait_event(ready)
                 lvl, r, done, small = bound.auto_level(), None, None, None
-                if bound.tc_ok and lvl < _engine.LEVEL_SIMT:
+                tc = bound.tc_ok and lvl < _engine.LEVEL_SIMT
+                if tc:
                     with torch.cuda.device(dev):
-                        r = bound.two_pass(N, mask, grid_mode, lvl, False)     # queued behind the previous sample's passes
+                        ctx = bound.two_pass_begin(N, mask, grid_mode, lvl, False)   # pass 1, queued behind the previous sample's passes
+                if pending is not None:
+                    finish_passes(pending)           # the previous sample's volumes go to the mesh worker meanwhile
+                if tc:
+                    with torch.cuda.device(dev):
+                        r = bound.two_pass_end(ctx)  # (reads the fast pass's list sizes,) re-grid, pass 2
                         # flags (exact in f64: int32 words / f32 bit patterns), lattice and bbox in one small tensor
                         small = torch.cat([bound.pending_flags().double(), r["grid"][0].double(), r["minmax"][0].double()])
                         done = torch.cuda.Event()
                         done.record(torch.cuda.current_stream(dev))
-                if pending is not None:
-                    finish_passes(pending)
                 pending = (idx, dev, bound, lvl, r, prefix, done, small)
                 n += 1
             if pending is not None and not errors:

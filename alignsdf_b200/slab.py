@@ -91,13 +91,18 @@ def _peer(group, r):
     return r if group is None else dist.get_global_rank(group, r)
 
 
+_SIGN = {}
+
+
 def reduce_bbox(box: torch.Tensor, flags: torch.Tensor = None, group=None):
     """Global bbox from per-rank {min x3, max x3} x2, and the elementwise MAX of the flag words, with a single MIN
     all-reduce (maxima travel negated).  -> (box int32[12], flags int32[N_FLAGS])"""
     b = box.reshape(-1).to(torch.int32)
     if flags is None:
         flags = torch.zeros(N_FLAGS, dtype=torch.int32, device=b.device)
-    sign = torch.tensor([1, 1, 1, -1, -1, -1] * 2 + [-1] * N_FLAGS, dtype=torch.int32, device=b.device)
+    sign = _SIGN.get(b.device)                 # cached on the device: a pageable H2D copy would wait for the stream
+    if sign is None:
+        sign = _SIGN[b.device] = torch.tensor([1, 1, 1, -1, -1, -1] * 2 + [-1] * N_FLAGS, dtype=torch.int32, device=b.device)
     packed = torch.cat([b, flags.to(torch.int32)]) * sign
     dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
     packed = packed * sign
