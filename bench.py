@@ -255,10 +255,13 @@ def main():
     launches = engine.LAUNCHES["count"] - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    k1 = {}
+    k1, k1_total_ms = {}, 0.0
     for kind, nq, a, b in engine.KERNEL_EVENTS:
-        if nq >= N ** 3 // max(world, 1) // 2:          # grid passes only (not the calibration launches)
-            k1.setdefault(kind, []).append((a.elapsed_time(b), nq))
+        if nq > 4 * engine.CALIB_POINTS:                 # everything but the calibration launches
+            t_k = a.elapsed_time(b)
+            k1_total_ms += t_k
+            if nq >= N ** 3 // max(world, 1) // 2:       # the grid passes themselves
+                k1.setdefault(kind, []).append((t_k, nq))
     mc = [(nb, a.elapsed_time(b) + c.elapsed_time(d)) for nb, a, b, c, d in engine.MC_EVENTS]
     engine.KERNEL_EVENTS = engine.MC_EVENTS = None
     kinds_used = sorted(set().union(*[b.kinds_used for b in bounds]))
@@ -369,6 +372,8 @@ def main():
                         l2="outputs (2 x 67 MB per pass) exceed L2; the 4 MB weight stream is L2-resident by design",
                         meshes_per_s=K / (ms * 1e-3), decoder_evals_Mps=2 * value),
             kernel=dict(selected=product_kind, kinds_launched=kinds_used, calibration_err=eng.calib,
+                        bbox_pass=("f16x1 (single fp16 product) with sign threshold tau = %.3e + exact re-evaluation of "
+                                   "the points within tau of zero" % eng.fast_tau()) if eng.fast_tau() else product_kind,
                         stats=dict(engine.STATS)),
             e2e=dict(value=e2e_value, unit="Mq/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes[0],
                      ms_per_step=e2e_ms / K, meshes_per_s=K / (e2e_ms * 1e-3)),
@@ -388,22 +393,36 @@ def main():
         if check is not None:
             line["check"] = check
         if k1:
-            kind = max(k1, key=lambda k: len(k1[k]))
-            tms = sum(t for t, _ in k1[kind]) / len(k1[kind])
-            nq = sum(q for _, q in k1[kind]) / len(k1[kind])
-            ach = nq * F_MIN / (tms * 1e-3) / 1e12
-            # issued tensor work in fp16-MMA time on padded shapes: 3 fp16 products, or 1 fp16 + 2 fp8 at twice the rate
-            issued = ach * (2.0 if kind == "f16+2xe4m3" else 3.0) * (2 * 2 * 524288) / F_MIN
-            line["roofline"] = dict(bound="tensor", kernel=f"tc_eval_kernel<{kind}>", achieved=ach, peak=peaks["tflops"],
-                                    unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=NCU_TRAFFIC_BYTES,
+            # the step's tensor-core work: both grid passes (pass 1 on the single-product kind + exact
+            # re-evaluation of the shell around the surface once the decoder has an error bound for it; pass 2 on the
+            # calibrated kind) over ALL tensor-core kernel time of the step, in algorithmic FLOPs of the two passes
+            per_kind = {k: dict(ms_per_launch=sum(t for t, _ in v) / len(v), launches=len(v),
+                                queries_per_launch=sum(q for _, q in v) / len(v)) for k, v in k1.items()}
+            nq_step = 2.0 * N ** 3 / world                   # queries of this rank per step
+            tms = k1_total_ms / K
+            ach = nq_step * F_MIN / (tms * 1e-3) / 1e12
+            p2 = k1.get(product_kind)
+            line["roofline"] = dict(bound="tensor",
+                                    kernel="tc_eval_kernel: pass 1 <%s>%s, pass 2 <%s>" % (
+                                        "f16x1" if "f16x1" in k1 else product_kind,
+                                        " + exact re-evaluation of the shell" if "f16x1" in k1 else "", product_kind),
+                                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"],
+                                    traffic=NCU_TRAFFIC_BYTES,
                                     traffic_note="dram__bytes_read+write of one 256^3 launch, ncu --set full "
                                                  "(profiles/); algorithmic HBM bytes = 8 B/query",
-                                    ms_per_launch=tms, queries_per_launch=nq, flop_per_query=F_MIN,
-                                    issued_tflops_f16_equiv=issued, frac_of_burst=ach / peaks["tflops_burst"],
-                                    peak_source=peaks["source"], Mq_per_s_kernel=nq / (tms * 1e-3) / 1e6,
-                                    ms_per_launch_minmax=[min(t for t, _ in k1[kind]), max(t for t, _ in k1[kind])],
-                                    launches_timed=len(k1[kind]),
-                                    other_kinds={k: sum(t for t, _ in v) / len(v) for k, v in k1.items() if k != kind})
+                                    tensor_kernel_ms_per_step=tms, queries_per_step=nq_step, flop_per_query=F_MIN,
+                                    frac_of_burst=ach / peaks["tflops_burst"], peak_source=peaks["source"],
+                                    per_kind=per_kind)
+            if p2:
+                t2 = sum(t for t, _ in p2) / len(p2)
+                q2 = sum(q for _, q in p2) / len(p2)
+                a2 = q2 * F_MIN / (t2 * 1e-3) / 1e12
+                # issued tensor work in fp16-MMA time on padded shapes: 3 fp16 products, or 1 fp16 + 2 fp8 at twice the rate
+                issued = a2 * (2.0 if product_kind == "f16+2xe4m3" else 3.0) * (2 * 2 * 524288) / F_MIN
+                line["roofline"]["exact_pass"] = dict(kernel=f"tc_eval_kernel<{product_kind}>", ms_per_launch=t2,
+                                                      queries_per_launch=q2, achieved=a2, frac=a2 / peaks["tflops"],
+                                                      issued_tflops_f16_equiv=issued,
+                                                      Mq_per_s_kernel=q2 / (t2 * 1e-3) / 1e6)
         if mc:
             nb = sum(b for b, _ in mc) / len(mc)
             tm = sum(t for _, t in mc) / len(mc)

@@ -16,7 +16,15 @@ dev = torch.device("cuda")
 dec = synthetic.make_decoder(0, init=init)
 s = synthetic.make_sample(0).to(dev)
 bound = engine.get_engine(dec, dev).bind(s.latent, s.specs, s.mano_results, s.obj_results)
-for _ in range(3):
-    bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path=path)
+if path == "f1":          # the bounding-box pass on the single-product kind (after one calibration)
+    from alignsdf_b200 import _lib
+    bound._calibrate(); bound.verify()
+    q = engine.make_query(_lib.QUERY_GRID_REFERENCE, N, 0, N ** 3, 2.0 / (N - 1), (-1.0, -1.0, -1.0), bbox_mask=3)
+    for _ in range(3):
+        bound.fast_bbox_pass(engine.LEVEL_KIND[engine.get_engine(dec, dev).level], q, N ** 3, engine.new_bbox(dev),
+                             engine.get_engine(dec, dev).fast_tau())
+else:
+    for _ in range(3):
+        bound.eval_grid(N, 2.0 / (N - 1), [-1, -1, -1], bbox_mask=3, path=path)
 torch.cuda.synchronize()
 print("stats", engine.STATS)
