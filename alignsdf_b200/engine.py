@@ -49,7 +49,7 @@ CALIB_FULL_EVERY = 16        # ... and every n-th one after them (BoundSample._c
 FAST_BBOX = os.environ.get("ALIGNSDF_B200_FAST_BBOX", "1") != "0"
 FAST_TAU_FACTOR = 4.0
 FAST_TAU_MARGIN = 2.0
-FAST_AMB_FRACTION = 8        # ambiguous-list capacity: N^3 / this many entries per sample (16 B each)
+FAST_AMB_FRACTION = 8        # ambiguous-list capacity: 1/8 of the queried points per sample, 16 B each (fast_bbox_begin)
 STATS = {"f8_rejected": 0, "tc_to_simt": 0, "f8_launches": 0, "f16_launches": 0, "simt_launches": 0,
          "f1_launches": 0, "fast_bbox_passes": 0, "fast_bbox_redone": 0, "fast_bbox_ambiguous": 0}
 FALLBACKS = STATS                # old name
@@ -496,7 +496,9 @@ class BoundSample:
     def fast_bbox_begin(self, kind, q, n, box, tau, calibrate=False, grid=None):
         """First half of fast_bbox_pass: the F16X1 launch (asynchronous).  -> context for fast_bbox_end."""
         dev, S = self.device, self.S
-        cap = max(n // FAST_AMB_FRACTION, 1 << 14)
+        # a z-slab can hold far more than its share of the shell (a surface patch parallel to it): its list may take
+        # up to what 1/16 of the whole grid would
+        cap = max(n // FAST_AMB_FRACTION, min(n, int(q.N) ** 3 // 16), 1 << 14)
         amb = torch.empty((S, cap, 4), dtype=torch.float32, device=dev)
         cnt = torch.zeros(S, dtype=torch.int32, device=dev)
         self._fast_tau = float(tau)
@@ -558,7 +560,7 @@ class BoundSample:
         q1 = make_query(_GRID_MODES[mode], N, 0, n, voxel, (-1.0, -1.0, -1.0), bbox_mask=bbox_mask)
         box = new_bbox(dev, self.S)
         auto = self.engine.path == "auto" if calibrate is None else calibrate
-        tau = self.engine.fast_tau() if (auto and not keep_pass1 and not self.redo_fast) else None
+        tau = self.engine.fast_tau(N) if (auto and not keep_pass1 and not self.redo_fast) else None
         fast, p1h, p1o = None, None, None
         if tau is not None:
             fast = self.fast_bbox_begin(kind, q1, n, box, tau, calibrate=True)
@@ -646,11 +648,14 @@ class DecoderEngine:
         self.calib = dict(f8=None, f16=None, f1=None, tol=CALIB_TOL, points=CALIB_POINTS, samples=0, samples_full=0,
                           launched=0)   # worst error bounds seen; batches calibrated (against the fp32 kernel)
 
-    def fast_tau(self):
+    def fast_tau(self, N=None):
         """Sign threshold for a bounding-box pass on the single-product kind, or None while this decoder has no
-        measured error bound for it yet (its first sample runs pass 1 on the exact kind)."""
+        measured error bound for it yet (its first sample runs pass 1 on the exact kind) or the grid is too large
+        for the 30-bit indices of the ambiguous-point list."""
         e1 = self.calib.get("f1")
         if not FAST_BBOX or e1 is None or not np.isfinite(e1) or self.level >= LEVEL_SIMT:
+            return None
+        if N is not None and int(N) ** 3 > (1 << 30):
             return None
         return FAST_TAU_FACTOR * max(e1, 1e-7)
 

@@ -306,7 +306,7 @@ def gpu_backend(bound, N, grid_mode="reference", path=None, spread=False) -> Bac
         state["level"] = lvl = bound.auto_level(path, calibrate=False)
         box = engine.new_bbox(dev)
         auto = not forced and bound.tc_ok and lvl < engine.LEVEL_SIMT
-        tau = bound.engine.fast_tau() if (auto and not bound.redo_fast) else None
+        tau = bound.engine.fast_tau(N) if (auto and not bound.redo_fast) else None
         state["fast"] = tau is not None and end > begin
         if end > begin:
             q = engine.make_query(mode, N, begin, end, vs1, (-1.0, -1.0, -1.0), bbox_mask=mask)
