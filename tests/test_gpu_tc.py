@@ -270,9 +270,10 @@ def _exact_box(bound, N, kind, mask=3, begin=0, end=None):
     return q, box
 
 
-@pytest.mark.parametrize("init,gain,N", [("default", 1.0, 96), ("plain", 4.0, 64), ("engineered", 1.0, 80)])
-def test_fast_bounding_box_pass_equals_the_exact_pass(init, gain, N):
-    dec = synthetic.make_decoder(41, init=init, out_gain=gain)
+@pytest.mark.parametrize("kind_name,init,gain,N", [("separate", "default", 1.0, 96), ("separate", "plain", 4.0, 64),
+                                                   ("separate", "engineered", 1.0, 80), ("combined", "plain", 4.0, 64)])
+def test_fast_bounding_box_pass_equals_the_exact_pass(kind_name, init, gain, N):
+    dec = synthetic.make_decoder(41, kind_name, init=init, out_gain=gain)
     smp = [s.to(DEV) for s in synthetic.make_batch(2, base_seed=41)]
     eng = engine.get_engine(dec, DEV)
     bound = eng.bind_batch([(s.latent, s.specs, s.mano_results, s.obj_results) for s in smp])
