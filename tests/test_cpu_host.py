@@ -275,3 +275,53 @@ def test_ply_writer_from_device_style_face_records(tmp_path):
     trimesh_lite.export_ply_records(b, v[:0], rec[:0])          # empty mesh: header only
     rv, rf = mo.read_ply(b)
     assert rv.shape == (0, 3) and rf.shape[0] == 0
+
+
+def _bits(x):
+    return int(np.array([x], np.float32).view(np.int32)[0])
+
+
+def test_kernel_selection_logic_from_flag_words():
+    """BoundSample.decide: calibration error bounds and operand-range words -> kernel level (pure host logic; the
+    words come from the device, or MAX-reduced from all ranks of a slab group)."""
+    from alignsdf_b200 import engine
+    dec = synthetic.make_decoder(5)
+    s = synthetic.make_sample(5)
+    eng = engine.DecoderEngine(dec, "cuda")                      # no device work happens at construction
+    assert eng.level == engine.LEVEL_F8 and eng.fast_tau() is None
+
+    def fresh():
+        b = eng.bind(s.latent, s.specs, s.mano_results, s.obj_results)
+        b._calib = object()                                      # "a calibration result is pending"
+        return b
+    # benign sample: fp16 + e4m3 accepted; its single-product error becomes the decoder's bound
+    b = fresh()
+    assert b.decide([0, 0, _bits(2e-6), _bits(2e-7), _bits(4e-5)]) == engine.LEVEL_F8
+    assert eng.level == engine.LEVEL_F8 and abs(eng.calib["f1"] - 4e-5) < 1e-9
+    assert abs(eng.fast_tau() - engine.FAST_TAU_FACTOR * 4e-5) < 1e-9 and eng.fast_tau(2048) is None
+    # a fast bounding-box pass whose threshold this sample's own error does not respect is void
+    b = fresh()
+    b._fast_tau = 1e-4
+    assert b.decide([0, 0, _bits(2e-6), _bits(2e-7), _bits(9e-5)]) == engine.LEVEL_F8 and b.redo_fast
+    b = fresh()
+    b._fast_tau = 4e-4
+    b.decide([0, 0, _bits(2e-6), _bits(2e-7), _bits(9e-5)])
+    assert not b.redo_fast
+    # e4m3 operand range exceeded on some rank -> all-fp16 kind, for good
+    b = fresh()
+    assert b.decide([1, 0, 0, 0, 0]) == engine.LEVEL_F16 and eng.level == engine.LEVEL_F16
+    # calibration rejects both tensor-core kinds (also NaN) -> fp32 kernel
+    eng2 = engine.DecoderEngine(dec, "cuda")
+    b = eng2.bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    b._calib = object()
+    assert b.decide([0, 0, _bits(3e-5), _bits(float("nan")), _bits(1e-3)]) == engine.LEVEL_SIMT
+    assert eng2.level == engine.LEVEL_SIMT and engine.STATS["tc_to_simt"] >= 1
+    # a bind failure (operands do not fit fp16) leaves only the fp32 kernel
+    eng3 = engine.DecoderEngine(dec, "cuda")
+    assert eng3.bind(s.latent, s.specs, s.mano_results, s.obj_results).decide([2, 0, 0, 0, 0]) == engine.LEVEL_SIMT
+    # a forced path is not overridden (sticky level untouched)
+    eng4 = engine.DecoderEngine(dec, "cuda")
+    eng4.path = "f8"
+    b = eng4.bind(s.latent, s.specs, s.mano_results, s.obj_results)
+    b._calib = object()
+    assert b.decide([0, 0, _bits(3e-5), _bits(1e-7), 0]) == engine.LEVEL_F16 and eng4.level == engine.LEVEL_F8

@@ -72,6 +72,52 @@ def _oracle_backend(dec, sample, N):
     return slab.Backend(pass1, regrid, pass2, mc_count, mc_emit, torch.device("cpu"))
 
 
+def _redo_worker(rank, world, port, name, out_dir):
+    """A backend whose flags reject the kernel kind on ONE rank only, once: every rank must repeat the sample."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        meta, g, dec, sample = helpers.load_case(name)
+        N = meta["N"]
+        be = _oracle_backend(dec, sample, N)
+        calls = dict(pass1=0, decide=[])
+        inner1 = be.pass1
+
+        def pass1(begin, end, mask):
+            calls["pass1"] += 1
+            box, flags = inner1(begin, end, mask)
+            if calls["pass1"] == 1 and rank == 1:
+                flags[0] = 1                           # "an activation left the e4m3 range" on rank 1's slab only
+            return box, flags
+
+        def decide(flags):
+            calls["decide"].append(list(flags))
+            return flags[0] != 0                       # repeat iff ANY rank raised the word
+
+        be.pass1, be.decide = pass1, decide
+        res = slab.reconstruct_slab(be, N, rank, world, keep_fields=True)
+        assert calls["pass1"] == 2 and [f[0] for f in calls["decide"]] == [1, 0], calls
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "redo.npz"), hand_f=res["meshes"]["hand"][2].numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_rejected_kernel_kind_on_one_rank_repeats_the_sample_on_all(tmp_path):
+    name = "sep_both9_n24"
+    mp.spawn(_redo_worker, args=(2, 29500 + os.getpid() % 2000 + 31, name, str(tmp_path)), nprocs=2, join=True)
+    meta, g, dec, sample = helpers.load_case(name)
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        res = orc.two_pass_field(sd, orc.decoder_cfg(dec), sample.latent, sample.specs, sample.mano_results,
+                                 sample.obj_results, meta["N"])
+    _, f, _ = mo.marching_cubes(res["hand"].numpy(), 0.0, [float(res["voxel"])] * 3)
+    assert np.array_equal(np.load(tmp_path / "redo.npz")["hand_f"], f)
+
+
 def _worker(rank, world, port, name, out_dir, spread):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
