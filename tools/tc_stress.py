@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from alignsdf_b200 import engine, synthetic  # noqa: E402
 
-PATH = sys.argv[2] if len(sys.argv) > 2 else "tc2"
+PATH = sys.argv[2] if len(sys.argv) > 2 else "f8"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 dev = torch.device("cuda")
 dec = synthetic.make_decoder(0)
