@@ -28,3 +28,17 @@ s2 = synthetic.make_batch(2)[1].to(dev)
 vols = amesh.sdf_volumes(dec, s2.latent, s2.mano_results, s2.obj_results, s2.specs, N, keep_pass1=False)
 print("fast bbox pass:", vols["bound"].kinds_used)
 print("stats", engine.STATS)
+# marching cubes on a volume wide enough for the interior-tile path of mc_classify (128-point rows, 17 planes)
+ax = [torch.linspace(-1, 1, n, device=dev) for n in (40, 24, 264)]
+g = torch.meshgrid(*ax, indexing="ij")
+vol = (g[0] ** 2 + g[1] ** 2 + 0.3 * g[2] ** 2).sqrt() - 0.7 + 0.05 * torch.sin(9 * g[2])
+mc = engine.marching_cubes(vol.contiguous(), 0.0, [0.1] * 3, want_keys=True)
+print("mc", tuple(mc["verts"].shape), tuple(mc["faces"].shape))
+# nearest neighbour + PixelAlign
+from alignsdf_b200.deep_sdf.metrics.icp_trans_scale import nn_search  # noqa: E402
+a, b = torch.rand(777, 3, device=dev, dtype=torch.float64), torch.rand(2050, 3, device=dev, dtype=torch.float64)
+print("nn", int(nn_search(a, b).sum()))
+sp = synthetic.make_sample(3, pixel_align=(10, 12)).to(dev)
+bp = engine.get_engine(dec, dev).bind(sp.latent, sp.specs, sp.mano_results, sp.obj_results, cam_intr=sp.cam_intr)
+hp, op, _ = bp.eval_points(torch.rand(100, 3, device=dev) * 3 - 1.5)
+print("pixel align", float(hp.min()), float(op.max()))
