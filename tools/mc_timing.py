@@ -13,7 +13,7 @@ dev = torch.device("cuda")
 dec = synthetic.make_decoder(0, init=os.environ.get("MC_DECODER", "engineered"))
 s = synthetic.make_sample(0).to(dev)
 vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, N)
-vol = vols["hand"].contiguous()
+vol = vols[os.environ.get("MC_SURFACE", "hand")].contiguous()
 vs = float(vols["voxel"])
 L = _lib.lib()
 p = _lib.McParams()
