@@ -272,7 +272,8 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
     image): the two grid passes of sample i+1 run while a worker thread extracts, filters, reads back and
     writes the meshes of sample i on a second CUDA stream, so the host-side stages no longer leave the GPU
     idle between samples.  ``samples``: iterable of objects with ``latent``, ``mano_results``,
-    ``obj_results``, ``specs`` (host or CUDA tensors); ``filenames``: output prefixes.  Same files and
+    ``obj_results``, ``specs`` and, for PixelAlign samples, ``cam_intr`` (host or CUDA tensors); ``filenames``:
+    output prefixes.  Same files and
     meshes as the one-call-per-sample loop; returns the list of ``{"hand": mesh, "obj": mesh}`` dicts."""
     import queue
     import threading
@@ -326,7 +327,9 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
             latent = to(smp.latent)
             mano = None if smp.mano_results is None else {k: to(v) for k, v in smp.mano_results.items()}
             obj = None if smp.obj_results is None else {k: to(v) for k, v in smp.obj_results.items()}
-            bound = _engine.get_engine(decoder, dev).bind(latent, smp.specs, mano, obj)
+            cam = getattr(smp, "cam_intr", None)         # PixelAlign samples
+            bound = _engine.get_engine(decoder, dev).bind(latent, smp.specs, mano, obj,
+                                                          cam_intr=None if cam is None else to(cam))
             lvl = bound.auto_level()                     # starts the calibration run as well
             if lvl < _engine.LEVEL_SIMT:
                 bound.tc_blocks(_engine.LEVEL_KIND[lvl], 2.0)    # P tiles built on the device, ahead of the sample's turn
@@ -364,6 +367,7 @@ def create_meshes_pipelined(decoder, samples, filenames, N=256, hand_branch=True
                 smp = samples[idx]
                 vols = sdf_volumes(decoder, bound.inputs[0][0], bound.inputs[0][2], bound.inputs[0][3], smp.specs, N,
                                    hand_branch, obj_branch, False, dev, grid_mode, bound=bound, keep_pass1=False)
+                vols = {k: vols[k] for k in ("hand", "obj", "voxel", "origin", "bound")}
                 done = torch.cuda.Event()
                 done.record(torch.cuda.current_stream(dev))
         work.put((idx, vols, done, prefix))

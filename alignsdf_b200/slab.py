@@ -374,7 +374,7 @@ def create_mesh_combined_decoder_slab(hand_branch, obj_branch, cls_branch, decod
     from .trimesh_lite import Mesh, largest_watertight_component_mc
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = engine._device_of(latent_vec)
-    bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results)
+    bound = engine.get_engine(decoder, dev).bind(latent_vec, specs, mano_results, obj_results, cam_intr=cam_intr)
     be = gpu_backend(bound, N, grid_mode, spread=spread)
     which = tuple(t for t, use in (("hand", hand_branch), ("obj", obj_branch)) if use)
     res = reconstruct_slab(be, N, rank, world, hand_branch, obj_branch, which, group, spread=spread)

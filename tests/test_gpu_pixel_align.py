@@ -65,3 +65,17 @@ def test_create_mesh_with_pixel_align(tmp_path):
         has_surface = bool((g["pass2_" + tag] < 0).any() and (g["pass2_" + tag] >= 0).any())
         assert (res[tag] is not None) == has_surface
         assert os.path.exists(tmp_path / f"pa_{tag}.ply") == has_surface
+
+
+def test_pipelined_batch_api_with_pixel_align(tmp_path):
+    meta, g, dec, sample = helpers.load_case("sep_pa_both9_n12")
+    res = amesh.create_meshes_pipelined(dec, [sample, sample], [str(tmp_path / "a"), str(tmp_path / "b")], N=meta["N"],
+                                        device=DEV)
+    one = amesh.create_mesh_combined_decoder(True, True, False, dec, *[getattr(helpers.to_cuda(sample), k) for k in
+                                             ("latent", "mano_results", "obj_results", "cam_intr", "specs")],
+                                             str(tmp_path / "c"), N=meta["N"])
+    for r in res:
+        for tag in ("hand", "obj"):
+            assert (r[tag] is None) == (one[tag] is None)
+            if r[tag] is not None:
+                assert np.array_equal(r[tag].vertices, one[tag].vertices) and np.array_equal(r[tag].faces, one[tag].faces)
