@@ -5,6 +5,8 @@ and side effects), backed by the CUDA library.
     get_higher_res_cube            <-> utils/mesh.py:198-256
     convert_sdf_samples_to_ply     <-> utils/mesh.py:331-399
     write_verts_label_to_npz       <-> utils/mesh.py:281-297
+    write_verts_label_to_obj       <-> utils/mesh.py:258-278       (viz)
+    write_color_labeled_ply        <-> utils/mesh.py:300-329       (viz)
 
 Differences, all additive: the functions accept CUDA tensors and keep volumes on the
 device; ``create_mesh_combined_decoder`` additionally *returns* the meshes (the reference
@@ -163,6 +165,46 @@ def write_verts_label_to_npz(pytorch_3d_xyz_tensor, pytorch_label_tensor, npz_fi
     np.savez(npz_filename_out, points=pts, labels=labels)
 
 
+# colours of the six hand-part labels in the label visualisation (utils/mesh.py:315-320)
+_PART_COLOR = np.array([[13, 212, 128], [250, 70, 42], [131, 66, 37], [78, 137, 54], [187, 246, 163], [67, 220, 74]],
+                       dtype=np.uint8)
+
+
+def _label_points(pytorch_3d_xyz_tensor, offset, scale):
+    pts = pytorch_3d_xyz_tensor.data.cpu().numpy()
+    if scale is not None:
+        pts = pts * scale
+    if offset is not None:
+        pts = pts + offset
+    return pts
+
+
+def write_verts_label_to_obj(pytorch_3d_xyz_tensor, pytorch_label_tensor, obj_filename_out, offset=None, scale=None):
+    """``viz`` output of the label pass (utils/mesh.py:258-278): one ``v x y z g g g`` line per marching-cubes vertex,
+    grey level = 45 x label."""
+    pts = _label_points(pytorch_3d_xyz_tensor, offset, scale)
+    grey = pytorch_label_tensor.cpu().numpy() * 45.0
+    with open(obj_filename_out, "w") as fp:
+        fp.write("".join("v %.4f %.4f %.4f %.2f %.2f %.2f\n" % (p[0], p[1], p[2], c, c, c) for p, c in zip(pts, grey)))
+
+
+def write_color_labeled_ply(pytorch_3d_xyz_tensor, numpy_faces, pytorch_label_tensor, ply_filename_out, offset=None,
+                            scale=None):
+    """``viz`` output of the label pass (utils/mesh.py:300-329 + utils/customized_export_ply.py): ASCII PLY of the raw
+    marching-cubes mesh with one RGBA colour per vertex (the part colour of its label, alpha 255)."""
+    pts = _label_points(pytorch_3d_xyz_tensor, offset, scale)
+    rgb = _PART_COLOR[pytorch_label_tensor.cpu().numpy().astype(np.int32)]
+    faces = np.asarray(numpy_faces.cpu().numpy() if isinstance(numpy_faces, torch.Tensor) else numpy_faces).reshape(-1, 3)
+    head = ("ply\nformat ascii 1.0\n"
+            f"element vertex {len(pts)}\nproperty float x\nproperty float y\nproperty float z\n"
+            "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n"
+            f"element face {len(faces)}\nproperty list uchar int vertex_indices\nend_header\n")
+    with open(ply_filename_out, "w") as fp:
+        fp.write(head)
+        fp.write("".join("%f %f %f %d %d %d 255\n" % (p[0], p[1], p[2], c[0], c[1], c[2]) for p, c in zip(pts, rgb)))
+        fp.write("".join("3 %d %d %d\n" % (f[0], f[1], f[2]) for f in faces))
+
+
 def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None, launched=None):
     """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags); re-runs
     through the next safer kernel when they say so.  ``launched``: (level, result) of a two_pass already queued
@@ -255,7 +297,8 @@ def create_mesh_combined_decoder(hand_branch, obj_branch, cls_branch, decoder, l
             _, _, cls = bound.eval_points(v.to(bound.device), want_cls=True)
             out_labels = cls.float().cpu()
             if viz:
-                logging.warning("viz outputs (_label.obj, _color.ply) are not produced by alignsdf_b200")
+                write_verts_label_to_obj(v, out_labels, ply_filename_hand + "_label.obj", offset, scale)
+                write_color_labeled_ply(v, mesh_faces, out_labels, ply_filename_hand + "_color.ply", offset, scale)
             write_verts_label_to_npz(v, out_labels, ply_filename_hand + "_label.npz", offset, scale)
     if obj_branch:
         # the object mesh reuses the HAND call's offset/scale (utils/mesh.py:186-194)

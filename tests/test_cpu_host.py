@@ -325,3 +325,16 @@ def test_kernel_selection_logic_from_flag_words():
     b = eng4.bind(s.latent, s.specs, s.mano_results, s.obj_results)
     b._calib = object()
     assert b.decide([0, 0, _bits(3e-5), _bits(1e-7), 0]) == engine.LEVEL_F16 and eng4.level == engine.LEVEL_F8
+
+
+def test_label_visualisation_files_equal_the_reference(tmp_path):
+    """viz outputs of the label pass (utils/mesh.py:258-278,300-329) byte for byte against files written by the
+    reference's own functions (oracle/make_golden_viz.py)."""
+    from alignsdf_b200 import mesh as amesh
+    g = np.load(os.path.join(helpers.GOLD, "viz_label.npz"))
+    pts, labels = torch.from_numpy(g["points"]), torch.from_numpy(g["labels"])
+    for tag, off, sc in (("plain", None, None), ("moved", g["offset"], g["scale"])):
+        amesh.write_verts_label_to_obj(pts, labels, str(tmp_path / "a.obj"), off, sc)
+        amesh.write_color_labeled_ply(pts, g["faces"], labels, str(tmp_path / "a.ply"), off, sc)
+        assert open(tmp_path / "a.obj", "rb").read() == g[f"obj_{tag}"].tobytes()
+        assert open(tmp_path / "a.ply", "rb").read() == g[f"ply_{tag}"].tobytes()

@@ -279,7 +279,7 @@ def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
     prefix = str(tmp_path / "img0")
     res = amesh.create_mesh_combined_decoder(hb, ob, label, dec, s.latent, s.mano_results, s.obj_results,
                                              None, s.specs, prefix, N=meta["N"], max_batch=2 ** 18,
-                                             label_out=label)
+                                             label_out=label, viz=label)
     vols = amesh.sdf_volumes(dec, s.latent, s.mano_results, s.obj_results, s.specs, meta["N"], hb, ob, cls_branch=label)
     vs = float(vols["voxel"]); org = vols["origin"].tolist()
     for tag, use in (("hand", hb), ("obj", ob)):
@@ -316,6 +316,13 @@ def test_create_mesh_combined_decoder_end_to_end(dev, tmp_path, name):
         clear = (top2[:, 0] - top2[:, 1]) > 1e-4                             # ties within fp32 noise may go either way
         assert clear.float().mean() > 0.99
         assert np.array_equal(lab["labels"][clear.numpy()], logits.argmax(1).float().numpy()[clear.numpy()])
+        # viz files (utils/mesh.py:258-278,300-329): one line per vertex; raw marching-cubes faces, coloured by label
+        obj_lines = open(prefix + "_hand_label.obj").read().splitlines()
+        assert len(obj_lines) == len(want_pts) and obj_lines[0].startswith("v ")
+        ply_lines = open(prefix + "_hand_color.ply").read().splitlines()
+        _, f_raw, _ = mo.marching_cubes(vols["hand"].cpu().numpy(), 0.0, [vs] * 3)
+        assert f"element vertex {len(want_pts)}" in ply_lines and f"element face {len(f_raw)}" in ply_lines
+        assert ply_lines[-1] == "3 %d %d %d" % tuple(f_raw[-1])
 
 
 def test_label_out_without_classifier_raises_like_reference(dev, tmp_path):
