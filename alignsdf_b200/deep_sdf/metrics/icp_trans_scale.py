@@ -10,8 +10,6 @@ the device -- instead of an SVD of the [6 n, 4] matrix.  There is no CPU path.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 

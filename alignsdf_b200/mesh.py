@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import logging
 import os
-import time
 
 import numpy as np
 import torch
@@ -205,11 +204,10 @@ def write_color_labeled_ply(pytorch_3d_xyz_tensor, numpy_faces, pytorch_label_te
         fp.write("".join("3 %d %d %d\n" % (f[0], f[1], f[2]) for f in faces))
 
 
-def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None, launched=None):
-    """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags); re-runs
-    through the next safer kernel when they say so.  ``launched``: (level, result) of a two_pass already queued
-    by the caller (run-ahead of the pipelined batch API)."""
-    lvl, r = launched if launched is not None else (bound.auto_level(path, calibrate=False), None)
+def _two_pass_verified(bound, N, mask, grid_mode, keep_pass1, path=None):
+    """bound.two_pass + the host check of its speculative parts (calibration, operand-range flags, threshold of
+    the fast bounding-box pass); re-runs through the next safer kernel / the exact pass when they say so."""
+    lvl, r = bound.auto_level(path, calibrate=False), None
     auto = (_engine._PATH_ALIASES.get(path, path) if path else bound.engine.path) == "auto"
     while True:
         if r is None:

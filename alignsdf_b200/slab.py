@@ -289,8 +289,6 @@ def gpu_backend(bound, N, grid_mode="reference", path=None, spread=False) -> Bac
     """Kernels of libalignsdf_b200.so on ``bound`` (an engine.BoundSample of ONE sample).  Nothing here waits for
     the GPU; the kernel kind is the decoder's current level, checked through the flags (``decide``).  ``spread``:
     the slab sizes anticipate reconstruct_slab(..., spread=True)."""
-    import ctypes as C
-
     from . import _lib, engine
     dev = bound.device
     mode = engine._GRID_MODES[grid_mode]

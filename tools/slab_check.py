@@ -4,7 +4,6 @@ Compares, stage by stage: lattice, per-slab fields, stitched raw mesh, final mes
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
