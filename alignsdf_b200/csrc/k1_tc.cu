@@ -250,7 +250,8 @@ __device__ __forceinline__ int nb_layer(int g) { return g < 4 ? 0 : (g < 6 ? 1 :
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 0 ? 0 : (layer == 2 ? 4 : 8); }
 __device__ __forceinline__ int buf_of(int g) { return g < 3 ? 0 : (g == 3 ? 1 : (g & 1)); }
 
-template <bool kF8, bool kDebug>
+// kMain (ASDF_TC_F16X1, only with kF8): the fp16 main product alone -- no correction tiles, UMMAs or operands
+template <bool kF8, bool kDebug, bool kMain = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval_kernel(const Args a) {
   // accumulation order inside an N block: F16X3 corrections first (accumulator truncation), F16_F8 interleaved
   // (shared-memory operand bandwidth); the packed weight stream (tc_pack.py) follows the same order
@@ -336,7 +337,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
           }
           for (int j = 0; j < n; ++j) {                                               // main phase / (hi, correction) pairs
             if (kCorrFirst) { push(mt); mt += kTileBytes; }
-            else { push(mt, a.main_only ? kTileBytes : 2 * kTileBytes); mt += 2 * kTileBytes; }   // (hi, correction) pair in one copy
+            else { push(mt, kMain ? kTileBytes : 2 * kTileBytes); mt += 2 * kTileBytes; }   // (hi, correction) pair in one copy
             if (g == kPTilesPerDecoder - 1 && has_next) {
               if (j == 2) push(ptile(smp_next, dec_next, 0));
               if (j == 5) push(ptile(smp_next, dec_next, 1));
@@ -365,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       // The whole warp walks the schedule (all values warp-uniform -> uniform registers); elect.sync inside the
       // wrappers picks the issuing lane.
       const uint32_t issue = 1u;
-      const bool main_only = a.main_only != 0;       // warp-uniform
+      constexpr bool main_only = kMain;
       uint32_t slot = 0, phase = 0, a_phase = 0, ap_phase = 0;
       // uses so far of accumulator buffer X / Y -- scalars, not an indexed array: an array goes to local memory
       // and its (per-thread) loads make the wait loops, and then every descriptor, look divergent to ptxas
@@ -592,7 +593,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_eval
       }
     };
     // ASDF_TC_F16X1 (main product only): no correction operands are computed or stored
-    const bool hi_only = a.main_only != 0;
+    constexpr bool hi_only = kMain;
     auto split32_hi = [&](const float* acc, float inv, uint32_t* hi) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -827,11 +828,11 @@ extern "C" int64_t asdf_tc_sample_bytes(void) { return asdf::tc::kSampleBytes; }
 
 namespace asdf {
 namespace tc {
-template <bool kF8, bool kDebug>
+template <bool kF8, bool kDebug, bool kMain = false>
 static int launch(const Args& a, unsigned grid, int smem, cudaStream_t stream) {
   // per device and cheap: set on every launch (one process may drive several devices)
-  ASDF_CUDA_CHECK(cudaFuncSetAttribute(tc_eval_kernel<kF8, kDebug>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_eval_kernel<kF8, kDebug><<<grid, kThreads, smem, stream>>>(a);
+  ASDF_CUDA_CHECK(cudaFuncSetAttribute(tc_eval_kernel<kF8, kDebug, kMain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_eval_kernel<kF8, kDebug, kMain><<<grid, kThreads, smem, stream>>>(a);
   ASDF_CUDA_CHECK(cudaGetLastError());
   return ASDF_OK;
 }
@@ -888,14 +889,16 @@ static int tc_eval_impl(const asdf_tc_launch* l, const asdf_query* q, void* stre
   if (debug_dev) {
     const char* e = getenv("ASDF_TC_DEBUG_FLAGS");
     a.dbg_flags = e ? atoi(e) : 0;
+    ASDF_REQUIRE(l->kind != ASDF_TC_F16X1, "asdf_tc_eval_debug: no debug instantiation of ASDF_TC_F16X1");
     return l->kind != ASDF_TC_F16X3 ? tc::launch<true, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream)
                                     : tc::launch<false, true>(a, grid, tc::kSmemBytesDebug, (cudaStream_t)stream);
   }
 #else
   ASDF_REQUIRE(!debug_dev, "asdf_tc_eval_debug: this library was built without ASDF_TC_DEBUG");
 #endif
-  return l->kind != ASDF_TC_F16X3 ? tc::launch<true, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream)
-                                  : tc::launch<false, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream);
+  if (l->kind == ASDF_TC_F16X1) return tc::launch<true, false, true>(a, grid, tc::kSmemBytes, (cudaStream_t)stream);
+  return l->kind == ASDF_TC_F16_F8 ? tc::launch<true, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream)
+                                   : tc::launch<false, false>(a, grid, tc::kSmemBytes, (cudaStream_t)stream);
 }
 
 extern "C" int asdf_tc_eval(const asdf_tc_launch* l, const asdf_query* q, void* stream) {
