@@ -267,6 +267,24 @@ def main():
     kinds_used = sorted(set().union(*[b.kinds_used for b in bounds]))
     product_kind = engine.LEVEL_NAMES[eng.level]
 
+    # ---------------- the same device-resident loop with pass 1 on the exact kind (transparency) ----------------
+    exact_bbox = None
+    if eng.fast_tau(N) is not None:
+        engine.FAST_BBOX = False
+        try:
+            for i in range(2):
+                step_device(i, bounds[i % S])
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for i in range(K):
+                step_device(i, bounds[i % S])
+            x1.record()
+            barrier()
+            exact_bbox = x0.elapsed_time(x1)
+        finally:
+            engine.FAST_BBOX = True
+
     # ---------------- 16 samples in ONE launch per pass (config #3; single GPU) ----------------
     batched = None
     if world == 1 and S >= 2 and N <= 256:
@@ -344,13 +362,13 @@ def main():
         barrier()
 
     # ---------------- max over ranks ----------------
-    t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_pipe_s * 1e3, exact_bbox or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         nb = torch.tensor([d2h_bytes[0]], dtype=torch.int64, device=dev)       # meshes are read back by two ranks
         dist.all_reduce(nb, op=dist.ReduceOp.SUM)
         d2h_bytes[0] = int(nb[0])
-    ms, e2e_ms, pipe_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_ms, pipe_ms, exact_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     queries = 2.0 * N ** 3 * K
     value = queries / (ms * 1e-3) / 1e6
     e2e_value = queries / (e2e_ms * 1e-3) / 1e6
@@ -388,6 +406,11 @@ def main():
             pipe["mode"] = (f"sample-parallel (dist_reconstruct.py:63-84): {K} samples dealt round-robin to {world} ranks, "
                             "no communication, end to end, max over ranks")
             line["sample_parallel"] = pipe
+        if exact_ms > 0:
+            line["exact_bbox_pass"] = dict(
+                value=queries / (exact_ms * 1e-3) / 1e6, unit="Mq/s", ms_per_step=exact_ms / K,
+                note="the same device-resident loop with ALIGNSDF_B200_FAST_BBOX=0: pass 1 on the exact kind instead of "
+                     "the single-product kind + exact re-evaluation of the shell (identical bounding boxes and meshes)")
         if batched is not None:
             line["batched"] = batched
         if check is not None:
