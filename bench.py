@@ -285,6 +285,20 @@ def main():
         finally:
             engine.FAST_BBOX = True
 
+    # ---------------- the all-fp16 kind (the fallback of the calibrated kind), one grid pass, for the record ----------------
+    f16x3_ms = None
+    if world == 1 and bounds[0].tc_ok:
+        from alignsdf_b200 import _lib
+        qf = engine.make_query(_lib.QUERY_GRID_REFERENCE, N, 0, N ** 3, 2.0 / (N - 1), (-1.0, -1.0, -1.0), bbox_mask=3)
+        for _ in range(2):
+            y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            y0.record()
+            bounds[0].launch_tc(engine.F16X3, qf, N ** 3, True, engine.new_bbox(dev))
+            y1.record()
+        torch.cuda.synchronize(dev)
+        f16x3_ms = y0.elapsed_time(y1)
+        bounds[0]._pending.clear()
+
     # ---------------- 16 samples in ONE launch per pass (config #3; single GPU) ----------------
     batched = None
     if world == 1 and S >= 2 and N <= 256:
@@ -392,7 +406,7 @@ def main():
             kernel=dict(selected=product_kind, kinds_launched=kinds_used, calibration_err=eng.calib,
                         bbox_pass=("f16x1 (single fp16 product) with sign threshold tau = %.3e + exact re-evaluation of "
                                    "the points within tau of zero" % eng.fast_tau()) if eng.fast_tau() else product_kind,
-                        stats=dict(engine.STATS)),
+                        f16x3_ms_per_launch=f16x3_ms, stats=dict(engine.STATS)),
             e2e=dict(value=e2e_value, unit="Mq/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes[0],
                      ms_per_step=e2e_ms / K, meshes_per_s=K / (e2e_ms * 1e-3)),
             gpu_launches=launches, clocks=clocks,
