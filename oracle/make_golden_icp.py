@@ -1,4 +1,5 @@
-"""Generate tests/golden/icp_*.npz by running the REAL reference's ICP_T_S class.  TEST INFRASTRUCTURE.
+"""Generate tests/golden/icp_*.npz by running the REAL reference's ICP_T_S class, and tests/golden/align_*.npz by
+running the REAL reference's chamfer.py alignment helpers (procrustes, procrustes_without_rot, icp).  TEST INFRASTRUCTURE.
 
 Runs only in the authoring container (needs /root/reference).  Shims: empty modules for the packages that are not installed
 (trimesh, plyfile, skimage, ...: the class only touches trimesh in sample_mesh / export, which are not called -- the
@@ -79,6 +80,58 @@ def main():
                             n_iter=len(errors), final_error=errors[-1], chamfer_after=cd)
         print(c["name"], "iterations", len(errors), "scale", float(np.asarray(ref.scale).reshape(-1)[0]),
               "final error", errors[-1], "chamfer", cd)
+    align_cases(out_dir)
+
+
+def rotation(axis, angle):
+    axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * K @ K
+
+
+ALIGN = [dict(name="align_a", seed=11, n=1200, scale=1.15, shift=(0.01, -0.02, 0.015), angle=0.20, noise=2e-4, thr=1e-5, cap=20),
+         dict(name="align_b", seed=12, n=800, scale=0.9, shift=(-0.03, 0.01, 0.0), angle=0.05, noise=1e-3, thr=1e-9, cap=4),
+         dict(name="align_c", seed=13, n=1500, scale=1.0, shift=(0.0, 0.0, 0.0), angle=0.0, noise=5e-4, thr=1e-12, cap=20)]
+
+
+def align_cases(out_dir):
+    """chamfer.py:61-180 of the reference on seeded clouds; ``thr`` below the file's 1e-5 default makes the loops run
+    more than two rounds (the clouds are in metres, costs ~1e-6); ``cap`` stops align_b before the two-sided loop has
+    shrunk both clouds onto single points (scale is free on both sides: with this cloud it collapses after 9 rounds,
+    and where it lands is rounding noise -- nothing to compare)."""
+    from deep_sdf.metrics import chamfer as ref              # the reference's own module (trimesh stubbed, unused here)
+    for c in ALIGN:
+        src, tgt = clouds(c["seed"], c["n"], c["n"] + 100, c["scale"], c["shift"], c["noise"])
+        tgt = tgt @ rotation((1.0, 2.0, -1.0), c["angle"]).T
+        g = np.random.default_rng(c["seed"] + 100)
+        paired = (c["scale"] * src) @ rotation((0.3, -1.0, 0.5), 2 * c["angle"] + 0.1).T + np.asarray(c["shift"]) \
+            + g.normal(scale=c["noise"], size=src.shape)
+        out = dict(source=src, target=tgt, paired=paired, thr=c["thr"], cap=c["cap"])
+        # one matched step, all three flavours
+        for tag, kw in (("refl", dict()), ("rigid", dict(reflection=False)), ("noscale", dict(scale=False, reflection=False)),
+                        ("notrans", dict(translation=False))):
+            m, t, cost = ref.procrustes(src, paired, **kw)
+            om, ot, ocost = icp_oracle.procrustes(src, paired, **kw)
+            assert np.allclose(om, m, rtol=1e-12, atol=1e-15) and np.allclose(ot, t, rtol=1e-12, atol=1e-15)
+            assert abs(ocost - cost) <= 1e-14 * max(1.0, abs(cost))
+            out["p_%s_matrix" % tag], out["p_%s_cost" % tag] = m, cost
+        m, t, cost = ref.procrustes_without_rot(src, paired)
+        om, ot, ocost = icp_oracle.procrustes_without_rot(src, paired)
+        assert np.allclose(om, m, rtol=1e-12, atol=1e-15) and np.allclose(ot, t, rtol=1e-12, atol=1e-15)
+        out["s_matrix"], out["s_cost"] = m, cost
+        # the two-sided loop, without and with rotation
+        for tag, rot in (("ts", False), ("tr", True)):
+            ta, tb, cost = ref.icp(src, tgt, threshold=c["thr"], max_iterations=c["cap"], rot=rot)
+            oa, ob, ocost, n_iter = icp_oracle.icp_two_sided(src, tgt, threshold=c["thr"], max_iterations=c["cap"], rot=rot)
+            assert np.allclose(oa, ta, rtol=1e-10, atol=1e-13) and np.allclose(ob, tb, rtol=1e-10, atol=1e-13), tag
+            assert abs(ocost - cost) <= 1e-12 * max(1.0, abs(cost))
+            out["icp_%s_a" % tag], out["icp_%s_b" % tag], out["icp_%s_cost" % tag], out["icp_%s_iters" % tag] = ta, tb, cost, n_iter
+        # the one-sided loop (trimesh.registration.icp restated; unpinned): stored from the ORACLE for regression only
+        total, moved, cost, n_iter = icp_oracle.registration_icp(src, tgt, threshold=c["thr"], max_iterations=c["cap"])
+        out["reg_matrix"], out["reg_cost"], out["reg_iters"] = total, cost, n_iter
+        np.savez_compressed(os.path.join(out_dir, c["name"] + ".npz"), **out)
+        print(c["name"], "two-sided iterations", int(out["icp_ts_iters"]), int(out["icp_tr_iters"]), "one-sided", n_iter,
+              "costs", float(out["icp_ts_cost"]), float(out["icp_tr_cost"]), cost)
 
 
 if __name__ == "__main__":

@@ -53,6 +53,57 @@ def test_icp_matches_the_reference_fixture(path):
     assert abs(float(np.asarray(icp2.scale).reshape(-1)[0]) - float(g["scale"][0])) <= 5e-3
 
 
+ALIGN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "align_*.npz")))
+
+
+@pytest.mark.parametrize("path", ALIGN, ids=[os.path.basename(p)[:-4] for p in ALIGN])
+def test_alignment_helpers_match_the_reference_fixture(path):
+    """chamfer.py:61-180 through the GPU neighbour search and device moments, against the outputs captured from the
+    reference's own functions (oracle/make_golden_icp.py)."""
+    g = np.load(path)
+    for tag, kw in (("refl", dict()), ("rigid", dict(reflection=False)), ("noscale", dict(scale=False, reflection=False)),
+                    ("notrans", dict(translation=False))):
+        m, moved, cost = gchamfer.procrustes(g["source"], g["paired"], **kw)
+        assert np.allclose(m, g["p_%s_matrix" % tag], rtol=1e-9, atol=1e-12), tag
+        assert abs(cost - float(g["p_%s_cost" % tag])) <= 1e-12
+        assert np.allclose(moved, icp_oracle.apply_matrix(g["source"], m), rtol=0, atol=1e-13)
+    m, _, cost = gchamfer.procrustes_without_rot(g["source"], g["paired"])
+    assert np.allclose(m, g["s_matrix"], rtol=1e-9, atol=1e-12) and abs(cost - float(g["s_cost"])) <= 1e-12
+    thr, cap = float(g["thr"]), int(g["cap"])
+    for tag, rot in (("ts", False), ("tr", True)):
+        a, b, cost = gchamfer.icp(g["source"], g["target"], threshold=thr, max_iterations=cap, rot=rot)
+        want = float(g["icp_%s_cost" % tag])
+        assert np.allclose(a, g["icp_%s_a" % tag], rtol=1e-7, atol=1e-10) and np.allclose(b, g["icp_%s_b" % tag], rtol=1e-7, atol=1e-10)
+        assert abs(cost - want) <= 1e-9 * want
+    total, moved, cost = gchamfer.registration_icp(g["source"], g["target"], threshold=thr, max_iterations=cap)
+    assert np.allclose(total, g["reg_matrix"], rtol=1e-7, atol=1e-10) and abs(cost - float(g["reg_cost"])) <= 1e-9 * float(g["reg_cost"])
+    assert np.allclose(moved, icp_oracle.apply_matrix(g["source"], total), rtol=0, atol=1e-12)
+
+
+def test_chamfer_with_rotation_fit(tmp_path):
+    """chamfer.py:199-203 (optim + rot) through compute_trimesh_chamfer, against the oracle on the same samples."""
+    rng = np.random.default_rng(2)
+    d = rng.normal(size=(400, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    import scipy.spatial
+    hull = scipy.spatial.ConvexHull(d)                                  # a closed triangle mesh on the unit sphere
+    gt = tl.Mesh(d * [0.08, 0.06, 0.05], hull.simplices.astype(np.int64))
+    ang = 0.12
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    pred = tl.Mesh(gt.vertices @ R.T * 1.05 + [0.004, -0.003, 0.002], gt.faces)
+    gt.export(str(tmp_path / "gt.ply"))
+    pred.export(str(tmp_path / "pred.ply"))
+    plain = gchamfer.compute_trimesh_chamfer(str(tmp_path / "gt.ply"), str(tmp_path / "pred.ply"), rng=np.random.default_rng(3))
+    fitted = gchamfer.compute_trimesh_chamfer(str(tmp_path / "gt.ply"), str(tmp_path / "pred.ply"), optim=True, rot=True,
+                                              rng=np.random.default_rng(3))
+    rng = np.random.default_rng(3)
+    src, _ = tl.sample_surface(tl.load(str(tmp_path / "pred.ply")), 30000, rng)
+    tgt, _ = tl.sample_surface(tl.load(str(tmp_path / "gt.ply")), 30000, rng)
+    _, aligned, _, _ = icp_oracle.registration_icp(src, tgt)
+    want = icp_oracle.chamfer(aligned, tgt)
+    assert abs(fitted - want) <= 1e-7 * want and fitted < plain
+
+
 def test_eval_mode_aligns_the_mesh_to_the_ground_truth_on_disk(tmp_path, monkeypatch):
     """utils/mesh.py:385-395 through the drop-in call: the written hand mesh is the ICP-aligned one, (trans, scale)
     equal the oracle's on the same surface samples, and the object mesh is moved by the hand's transform (:186-194)."""

@@ -67,3 +67,124 @@ def test_surface_samples_lie_on_the_faces_and_follow_their_area():
     assert uv.min() >= -1e-12 and (uv.sum(1) <= 1 + 1e-12).all()
     share = np.bincount(fi, minlength=4) / len(fi)
     assert np.abs(share - m.area_faces / m.area).max() <= 0.01
+
+
+# --- chamfer.py:13-180: the alignment helpers ---------------------------------------------------------------------------
+ALIGN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "align_*.npz")))
+FLAVOURS = (("refl", dict()), ("rigid", dict(reflection=False)), ("noscale", dict(scale=False, reflection=False)),
+            ("notrans", dict(translation=False)))
+
+
+@pytest.mark.parametrize("path", ALIGN, ids=[os.path.basename(p)[:-4] for p in ALIGN])
+def test_alignment_oracle_reproduces_the_reference(path):
+    g = np.load(path)
+    for tag, kw in FLAVOURS:
+        m, _, cost = icp_oracle.procrustes(g["source"], g["paired"], **kw)
+        assert np.allclose(m, g["p_%s_matrix" % tag], rtol=1e-12, atol=1e-15), tag
+        assert abs(cost - float(g["p_%s_cost" % tag])) <= 1e-14
+    m, _, cost = icp_oracle.procrustes_without_rot(g["source"], g["paired"])
+    assert np.allclose(m, g["s_matrix"], rtol=1e-12, atol=1e-15) and abs(cost - float(g["s_cost"])) <= 1e-14
+    for tag, rot in (("ts", False), ("tr", True)):
+        a, b, cost, n_iter = icp_oracle.icp_two_sided(g["source"], g["target"], threshold=float(g["thr"]), max_iterations=int(g["cap"]), rot=rot)
+        assert n_iter == int(g["icp_%s_iters" % tag])
+        assert np.allclose(a, g["icp_%s_a" % tag], rtol=1e-10, atol=1e-13) and np.allclose(b, g["icp_%s_b" % tag], rtol=1e-10, atol=1e-13)
+    total, _, cost, n_iter = icp_oracle.registration_icp(g["source"], g["target"], threshold=float(g["thr"]), max_iterations=int(g["cap"]))
+    assert n_iter == int(g["reg_iters"]) and np.allclose(total, g["reg_matrix"], rtol=1e-9, atol=1e-12)
+
+
+def check_two_sided(g, tag, a, b, cost):
+    want = float(g["icp_%s_cost" % tag])
+    assert np.allclose(a, g["icp_%s_a" % tag], rtol=1e-7, atol=1e-10) and np.allclose(b, g["icp_%s_b" % tag], rtol=1e-7, atol=1e-10)
+    assert abs(cost - want) <= 1e-9 * want
+
+
+def _host_only(monkeypatch):
+    """The drop-in's alignment helpers with the device swapped for the CPU and the CUDA neighbour search for a KD-tree:
+    checks the HOST logic (moments, matrices, loop / stopping rules) here; the real path is in test_gpu_metrics.py."""
+    import torch
+    from scipy.spatial import cKDTree
+    from alignsdf_b200.deep_sdf.metrics import chamfer as gch
+
+    def nn(query, ref, want_dist=False):
+        d, i = cKDTree(ref.numpy()).query(query.numpy(), 1)
+        return (torch.from_numpy(i), torch.from_numpy(d * d)) if want_dist else torch.from_numpy(i)
+    monkeypatch.setattr(gch, "_device", lambda device=None: torch.device("cpu"))
+    monkeypatch.setattr(gch, "nn_search", nn)
+    return gch
+
+
+@pytest.mark.parametrize("path", ALIGN, ids=[os.path.basename(p)[:-4] for p in ALIGN])
+def test_alignment_host_logic_matches_the_reference(path, monkeypatch):
+    gch = _host_only(monkeypatch)
+    g = np.load(path)
+    for tag, kw in FLAVOURS:
+        m, moved, cost = gch.procrustes(g["source"], g["paired"], **kw)
+        assert np.allclose(m, g["p_%s_matrix" % tag], rtol=1e-9, atol=1e-12), tag
+        assert abs(cost - float(g["p_%s_cost" % tag])) <= 1e-12
+        assert np.allclose(moved, gch.transform_points(g["source"], m), rtol=0, atol=1e-14)
+        assert np.array_equal(gch.procrustes(g["source"], g["paired"], return_cost=False, **kw), m)
+    m, _, cost = gch.procrustes_without_rot(g["source"], g["paired"])
+    assert np.allclose(m, g["s_matrix"], rtol=1e-9, atol=1e-12) and abs(cost - float(g["s_cost"])) <= 1e-12
+    for tag, rot in (("ts", False), ("tr", True)):
+        a, b, cost = gch.icp(g["source"], g["target"], threshold=float(g["thr"]), max_iterations=int(g["cap"]), rot=rot)
+        check_two_sided(g, tag, a, b, cost)
+    total, moved, cost = gch.registration_icp(g["source"], g["target"], threshold=float(g["thr"]), max_iterations=int(g["cap"]))
+    assert np.allclose(total, g["reg_matrix"], rtol=1e-7, atol=1e-10) and abs(cost - float(g["reg_cost"])) <= 1e-9 * float(g["reg_cost"])
+    assert np.allclose(moved, icp_oracle.apply_matrix(g["source"], total), rtol=0, atol=1e-12)
+
+
+def test_transform_points_conventions(monkeypatch):
+    gch = _host_only(monkeypatch)
+    p = np.random.default_rng(0).normal(size=(7, 3))
+    near = np.eye(4) + 5e-9
+    assert np.array_equal(gch.transform_points(p, near), p)                       # chamfer.py:48-50
+    m = np.eye(4)
+    m[:3, :3] *= 2.0
+    m[:3, 3] = [1.0, 2.0, 3.0]
+    assert np.allclose(gch.transform_points(p, m), 2 * p + [1.0, 2.0, 3.0], rtol=0, atol=1e-15)
+    assert np.allclose(gch.transform_points(p, m, translate=False), 2 * p, rtol=0, atol=1e-15)
+    assert gch.transform_points(np.zeros((0, 3)), m).shape == (0, 3)
+    with pytest.raises(ValueError):
+        gch.transform_points(p, np.eye(3))
+    with pytest.raises(ValueError):
+        gch.procrustes(p, p[:5])
+
+
+def test_chamfer_with_rotation_fit_runs_the_one_sided_loop(tmp_path, monkeypatch):
+    """chamfer.py:199-203 (optim + rot): a rotated, scaled, shifted copy of a mesh is pulled back onto it."""
+    gch = _host_only(monkeypatch)
+    m = _tetra()
+    sub = tl.Mesh(*_subdivide(m.vertices, m.faces, 3))
+    ang = 0.15
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    moved = tl.Mesh(sub.vertices @ R.T * 1.07 + [0.02, -0.01, 0.03], sub.faces)
+    sub.export(str(tmp_path / "gt.ply"))
+    moved.export(str(tmp_path / "pred.ply"))
+    plain = gch.compute_trimesh_chamfer(str(tmp_path / "gt.ply"), str(tmp_path / "pred.ply"), rng=np.random.default_rng(3))
+    fitted = gch.compute_trimesh_chamfer(str(tmp_path / "gt.ply"), str(tmp_path / "pred.ply"), optim=True, rot=True,
+                                         rng=np.random.default_rng(3))
+    rng = np.random.default_rng(3)
+    src, _ = tl.sample_surface(tl.load(str(tmp_path / "pred.ply")), 30000, rng)
+    tgt, _ = tl.sample_surface(tl.load(str(tmp_path / "gt.ply")), 30000, rng)
+    _, aligned, _, _ = icp_oracle.registration_icp(src, tgt)
+    want = icp_oracle.chamfer(aligned, tgt)
+    assert abs(fitted - want) <= 1e-8 * want and fitted < 0.2 * plain
+
+
+def _subdivide(v, f, rounds):
+    for _ in range(rounds):
+        mid = {}
+        v = [tuple(p) for p in v]
+        out = []
+
+        def m(i, j):
+            k = (min(i, j), max(i, j))
+            if k not in mid:
+                v.append(tuple((np.asarray(v[i]) + np.asarray(v[j])) / 2))
+                mid[k] = len(v) - 1
+            return mid[k]
+        for a, b, c in f:
+            ab, bc, ca = m(a, b), m(b, c), m(c, a)
+            out += [[a, ab, ca], [ab, b, bc], [ca, bc, c], [ab, bc, ca]]
+        v, f = np.asarray(v, np.float64), np.asarray(out, np.int64)
+    return v, f
