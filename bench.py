@@ -113,6 +113,17 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's torch-CPU path (oracle port)
 # ----------------------------------------------------------------------------
+def workload_config(N, samples, world):
+    """The ``config`` object of the JSON line: the workload only, identical in both arms (run-dependent figures
+    live under ``derived``)."""
+    return dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {samples} synthetic latents/poses",
+                decoder=DECODER_DESC, parallelism=f"zslab{world}" if world > 1 else "single",
+                l2="a step writes 4 volumes of %.0f MB (2 outputs x 2 passes) = %.0f MB per rank, which %s the 126 MB L2; "
+                   "the inputs of the path (4 MB weight stream, latent, pose) are L2-resident by design"
+                   % (4 * N ** 3 / world / 1e6, 16 * N ** 3 / world / 1e6,
+                      "exceeds" if 16 * N ** 3 / world > 126e6 else "does NOT exceed"))
+
+
 def cpu_reference_rate(N, chunks, warm=1):
     """M hand+obj queries/s of the reference's per-chunk work (grid -> embedding -> cat -> decoder,
     chunk = 2**18 points as in reconstruct.py:93) on all host cores."""
@@ -148,8 +159,7 @@ def run_reference(args):
         impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
         ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None, dtype="f32",
         data="synthetic",
-        config=dict(workload=f"{args.N}^3 hand+obj, 2 passes + 2 marching cubes, {args.samples} synthetic latents/poses",
-                    decoder=DECODER_DESC, chunk=2 ** 18),
+        config=workload_config(args.N, args.samples, args.gpus),
         cpu_baseline=dict(value=rate, unit="Mq/s", cores=cores, kind="port",
                           sample=f"{args.steps} chunks of 2^18 grid points of the {args.N}^3 workload through "
                                  "the oracle port of the reference's torch-CPU path (marching cubes excluded: "
@@ -398,11 +408,8 @@ def main():
             n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
             scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype=dtype,
             data="synthetic", impl="b200",
-            config=dict(workload=f"{N}^3 hand+obj, 2 passes + 2 marching cubes, {args.samples} synthetic latents/poses",
-                        decoder=DECODER_DESC, parallelism=f"zslab{world}" if world > 1 else "single",
-                        samples_visited=S,
-                        l2="outputs (2 x 67 MB per pass) exceed L2; the 4 MB weight stream is L2-resident by design",
-                        meshes_per_s=K / (ms * 1e-3), decoder_evals_Mps=2 * value),
+            config=workload_config(N, args.samples, world),
+            derived=dict(samples_visited=S, meshes_per_s=K / (ms * 1e-3), decoder_evals_Mps=2 * value),
             kernel=dict(selected=product_kind, kinds_launched=kinds_used, calibration_err=eng.calib,
                         bbox_pass=("f16x1 (single fp16 product) with sign threshold tau = %.3e + exact re-evaluation of "
                                    "the points within tau of zero" % eng.fast_tau()) if eng.fast_tau() else product_kind,

@@ -255,6 +255,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "Mq/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == dict(value=line["value"], unit="Mq/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    # both arms print the SAME config object (the driver compares them): one helper, no run-dependent figures in it
+    sys.path.insert(0, root)
+    import bench
+    assert line["config"] == bench.workload_config(64, 16, 1)
+    assert set(line["config"]) == {"workload", "decoder", "parallelism", "l2"}
+    src = open(os.path.join(root, "bench.py")).read()
+    assert src.count("config=workload_config(") == 2
 
 
 def test_ply_writer_from_device_style_face_records(tmp_path):
