@@ -16,7 +16,6 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass, field
 
-import numpy as np
 import torch
 
 from .decoders import CombinedDecoder, SeparateDecoder

@@ -24,7 +24,6 @@ Each function cites the reference lines it restates (paths relative to
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 
