@@ -64,7 +64,7 @@ def test_folded_network_matches_reference_golden(name):
     """packer.fold_decoder (latent -> bias, pose-align -> [out,3]) vs the reference (tol 1e-6)."""
     meta, g, dec, sample = helpers.load_case(name)
     if meta.get("pixel_align"):
-        pytest.skip("per-point latents are not folded (tests/test_gpu_pixel_align.py covers the kernel path)")
+        pytest.skip("per-point latents are not folded: test_pixel_align_projected_maps_match_reference_golden below")
     topo = packer.decoder_topology(dec)
     N = meta["N"]
     xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1])
@@ -345,3 +345,81 @@ def test_label_visualisation_files_equal_the_reference(tmp_path):
         amesh.write_color_labeled_ply(pts, g["faces"], labels, str(tmp_path / "a.ply"), off, sc)
         assert open(tmp_path / "a.obj", "rb").read() == g[f"obj_{tag}"].tobytes()
         assert open(tmp_path / "a.ply", "rb").read() == g[f"ply_{tag}"].tobytes()
+
+
+def _pa_taps_numpy(pa, xyz):
+    """Numpy statement of csrc/k1_simt.cu::pixel_align_taps in float32: per point 16 (map row, weight) taps."""
+    f = np.float32
+    P = pa["point_affine"].reshape(3, 4).astype(f)
+    C = pa["cam"].reshape(3, 4).astype(f)
+    x = xyz.astype(f)
+    c = (x @ P[:, :3].T + P[:, 3]).astype(f)
+    h = (c @ C[:, :3].T + C[:, 3]).astype(f)
+    size = f(pa["image_size"])
+    with np.errstate(all="ignore"):
+        u = (h[:, 0] / h[:, 2] / size * f(2) - f(1)).astype(f)
+        v = (h[:, 1] / h[:, 2] / size * f(2) - f(1)).astype(f)
+    fh, fw = pa["fh"], pa["fw"]
+    n = len(x)
+    ti = np.zeros((n, 16), np.int64)
+    tw = np.zeros((n, 16), f)
+    inside = (u >= -1) & (u <= 1) & (v >= -1) & (v <= 1)
+    ti[~inside, 0], tw[~inside, 0] = fh * fw, 1.0
+    ix, iy = (u + f(1)) * f(0.5) * f(fw - 1), (v + f(1)) * f(0.5) * f(fh - 1)
+    fx, fy = np.floor(ix), np.floor(iy)
+
+    def coeffs(t):
+        A = f(-0.75)
+        x0, x1, x2, x3 = t + f(1), t, f(1) - t, f(2) - t
+        return np.stack([((A * x0 - f(5) * A) * x0 + f(8) * A) * x0 - f(4) * A,
+                         ((A + f(2)) * x1 - (A + f(3))) * x1 * x1 + f(1),
+                         ((A + f(2)) * x2 - (A + f(3))) * x2 * x2 + f(1),
+                         ((A * x3 - f(5) * A) * x3 + f(8) * A) * x3 - f(4) * A], 1).astype(f)
+    cx, cy = coeffs((ix - fx).astype(f)), coeffs((iy - fy).astype(f))
+    for j in range(4):
+        for k in range(4):
+            xx, yy = fx.astype(np.int64) - 1 + k, fy.astype(np.int64) - 1 + j
+            ok = inside & (xx >= 0) & (xx < fw) & (yy >= 0) & (yy < fh)
+            ti[ok, 4 * j + k] = (yy * fw + xx)[ok]
+            tw[ok, 4 * j + k] = (cy[:, j] * cx[:, k])[ok]
+    return ti, tw, inside
+
+
+@pytest.mark.parametrize("name", ["sep_pa_both9_n12", "comb_pa_xyz3_n10"])
+def test_pixel_align_projected_maps_match_reference_golden(name):
+    """PixelAlign without a GPU: the host side of the path (pixel_align.setup: latent columns applied to the feature
+    map once per sample, projection folded into one affine map) + a numpy statement of the kernel's 16-tap bicubic
+    gather reproduce the REAL reference's pass-1 fields (utils/utils.py:536-566 through F.grid_sample)."""
+    from alignsdf_b200 import pixel_align
+    meta, g, dec, sample = helpers.load_case(name)
+    topo = packer.decoder_topology(dec)
+    N = meta["N"]
+    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
+    affine = packer.embedding_affine(sample.specs, sample.mano_results, sample.obj_results)
+    br = packer.fold_decoder(topo, None, sample.specs, sample.mano_results, sample.obj_results, affine=affine)
+    pa = pixel_align.setup(topo, sample.latent, sample.specs, sample.mano_results, sample.cam_intr, affine, False, "cpu")
+    ti, tw, inside = _pa_taps_numpy(pa, xyz)
+    assert inside.any() and (~inside).any()                      # both rules are exercised: bicubic taps and the mean feature
+    maps = pa["maps"].numpy()
+    outs = []
+    for b, branch in enumerate(br):
+        x = None
+        for l, fl in enumerate(branch.layers):
+            y = np.broadcast_to(fl.B, (len(xyz), fl.B.shape[0])).astype(np.float32).copy()
+            if fl.Wx is not None:
+                y += x @ fl.Wx.T
+            if fl.M is not None:
+                y += xyz.astype(np.float32) @ fl.M.T
+            if l in pa["layers"]:
+                G = maps[b, pa["layers"].index(l)]                # [fh fw + 1, npad]
+                y += np.einsum("pt,ptn->pn", tw, G[ti][:, :, :y.shape[1]])
+            if l == len(branch.layers) - 1:
+                y = np.tanh(np.tanh(y)) if topo.pre_tanh else np.tanh(y)
+            else:
+                assert fl.ln is None
+                y = np.maximum(y, 0)
+            x = y
+        outs.append(x)
+    hand, obj = (outs[0][:, 0], outs[1][:, 0]) if topo.kind == "separate" else (outs[0][:, 0], outs[0][:, 1])
+    assert np.abs(hand - g["pass1_hand"].reshape(-1)).max() <= 2e-6
+    assert np.abs(obj - g["pass1_obj"].reshape(-1)).max() <= 2e-6
