@@ -59,8 +59,10 @@ def _l4_fp32(x4, w4):
     return (parts[0] + parts[1]).astype(np.float32)
 
 
-def emulate(raw_static, raw_sample, xyz, kind=T.F16X3, n_dec=2, want_max=False, accum="exact"):
-    """``accum``: "exact" -- products accumulated in float64, rounded once per layer (the arithmetic the kernel
+def emulate(raw_static, raw_sample, xyz, kind=T.F16X3, n_dec=2, want_max=False, accum="exact", main_only=False):
+    """``main_only`` (with the F16_F8 streams): the F16X1 kind of the bounding-box pass -- the correction UMMAs are
+    skipped, everything else (P tile, scales, layer-3 epilogue) is unchanged.
+    ``accum``: "exact" -- products accumulated in float64, rounded once per layer (the arithmetic the kernel
     approximates); "hw" -- every UMMA in the kernel's issue order with the tensor core's accumulate rounding
     (_umma_hw; slow: use ~100 points)."""
     raw_static = np.asarray(raw_static, np.uint8)
@@ -118,7 +120,10 @@ def emulate(raw_static, raw_sample, xyz, kind=T.F16X3, n_dec=2, want_max=False, 
                         if hw:
                             for ks in range(4):
                                 add(acc, cols, a_hi[pos][:, 16 * ks:16 * ks + 16], bhi[:, 16 * ks:16 * ks + 16])
-                                add(acc, cols, a8[:, 32 * ks:32 * ks + 32], b8[:, 32 * ks:32 * ks + 32])
+                                if not main_only:
+                                    add(acc, cols, a8[:, 32 * ks:32 * ks + 32], b8[:, 32 * ks:32 * ks + 32])
+                        elif main_only:
+                            acc[:, cols] += a_hi[pos] @ bhi.T
                         else:
                             acc[:, cols] += a_hi[pos] @ bhi.T + a8 @ b8.T
                     continue

@@ -137,3 +137,47 @@ def test_bind_static_arrays_reproduce_the_host_fold(name):
         h = br[d].layers[1].B.shape[0]
         assert np.array_equal(b[1, :h].astype(np.float32), br[d].layers[1].B) and not b[1, h:].any()
         assert np.array_equal(b[3].astype(np.float32), br[d].layers[3].B)
+
+
+@pytest.mark.parametrize("name", ["sep_default_n32", "sep_both9_n24", "sep_plain_g1_n32", "comb_default_n16"])
+def test_single_product_kind_decides_every_sign_outside_its_threshold(name):
+    """The bounding-box pass: pass 1 runs on the fp16 main product alone (F16X1) and only trusts the sign
+    of values farther than tau = FAST_TAU_FACTOR x (largest calibration error) from zero; the rest is re-evaluated
+    exactly.  Emulated from the packed bytes on the WHOLE golden grid: (a) the calibration-sized sample bounds the
+    error of every grid point within the factor, (b) every value outside the threshold has the reference's sign, so the
+    box of {sdf < 0} is the reference's, (c) the ambiguous shell fits the list the kernel appends to."""
+    meta, g, dec, sample = helpers.load_case(name)
+    topo = packer.decoder_topology(dec)
+    raw, scales = tc_pack.pack_static_numpy(topo, tc_pack.F16_F8)
+    br = packer.fold_decoder(topo, sample.latent, sample.specs, sample.mano_results, sample.obj_results)
+    samp, _ = tc_pack.pack_sample_numpy(br, scales, 2.0, tc_pack.F16_F8)
+    N = meta["N"]
+    xyz = orc.grid_points(N, 2.0 / (N - 1), [-1, -1, -1]).numpy()
+    outs = emulate(raw, samp, xyz, tc_pack.F16_F8, len(topo.branches), main_only=True)
+    refs = [g["pass1_hand"].reshape(-1), g["pass1_obj"].reshape(-1)]
+    # calibration: 4096 random points of the cube against the exact evaluation (here: the oracle)
+    rng = np.random.default_rng(11)
+    cal = (rng.random((4096, 3)) * 2 - 1).astype(np.float32)
+    sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    import torch
+    with torch.no_grad():
+        rh, ro, _ = orc.decode_points(sd, orc.decoder_cfg(dec), sample.latent, torch.from_numpy(cal), sample.specs,
+                                      sample.mano_results, sample.obj_results)
+    ch, co = emulate(raw, samp, cal, tc_pack.F16_F8, len(topo.branches), main_only=True)
+    e1 = max(np.abs(ch - rh[:, 0].numpy()).max(), np.abs(co - ro[:, 0].numpy()).max())
+    tau = engine.FAST_TAU_FACTOR * max(float(e1), 1e-7)
+    shell = 0
+    for got, ref in zip(outs, refs):
+        assert np.abs(got - ref).max() <= tau, (name, float(np.abs(got - ref).max()), tau)       # (a)
+        assert (ref[got < -tau] < 0).all() and (ref[got > tau] >= 0).all()                       # (b)
+        # the merged rule of the fast pass reproduces the reference's negative set exactly
+        amb = np.abs(got) <= tau
+        negative = (got < -tau) | (amb & (ref < 0))
+        assert np.array_equal(negative, ref < 0)
+        shell += int(amb.sum())
+    # far more precise than needed for the sign, far less than the 1e-5 contract: that is why it only feeds the box
+    n = N ** 3
+    cap = max(n // engine.FAST_AMB_FRACTION, min(n, n // 16), 1 << 14)          # engine.BoundSample.fast_bbox_begin
+    assert shell <= cap, (name, shell, cap)                                      # (c)
+    print(f"{name}: e1 {e1:.2e} tau {tau:.2e} worst grid error {max(float(np.abs(a - b).max()) for a, b in zip(outs, refs)):.2e} "
+          f"shell {shell} of {2 * n} values (capacity {cap})")
