@@ -80,7 +80,8 @@ def export_ply_records(path, vertices, face_records):
 
 def load(path, process=False):
     """``trimesh.load(path, process=False)`` for the two formats the path meets: Wavefront OBJ (ground-truth meshes,
-    utils/mesh.py:390) and the binary little-endian PLY written by ``export_ply``.  Polygons are fan-triangulated."""
+    utils/mesh.py:390) and PLY (``_load_ply``: our own files, trimesh's, plyfile's; ascii or binary).  Polygons are
+    fan-triangulated."""
     path = str(path)
     if path.lower().endswith(".obj"):
         verts, faces = [], []
@@ -95,21 +96,128 @@ def load(path, process=False):
                         faces.append([idx[0], idx[k], idx[k + 1]])
         return Mesh(np.asarray(verts, np.float64).reshape(-1, 3), np.asarray(faces, np.int64).reshape(-1, 3))
     if path.lower().endswith(".ply"):
-        with open(path, "rb") as fh:
-            raw = fh.read()
-        end = raw.index(b"end_header\n") + len(b"end_header\n")
-        header = raw[:end].decode("ascii").split("\n")
-        if "format binary_little_endian 1.0" not in header:
-            raise ValueError(f"{path}: only binary little-endian PLY is supported")
-        nv = next(int(l.split()[-1]) for l in header if l.startswith("element vertex"))
-        nf = next(int(l.split()[-1]) for l in header if l.startswith("element face"))
-        props = [l for l in header if l.startswith("property") and "list" not in l]
-        if len(props) != 3:
-            raise ValueError(f"{path}: expected x, y, z float vertex properties only")
-        v = np.frombuffer(raw, "<f4", nv * 3, end).reshape(nv, 3)
-        rec = np.frombuffer(raw, np.dtype([("n", "u1"), ("idx", "<i4", (3,))]), nf, end + nv * 12)
-        return Mesh(v.astype(np.float64), rec["idx"].astype(np.int64))
+        return _load_ply(path)
     raise ValueError(f"unsupported mesh format: {path}")
+
+
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
+              "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def _load_ply(path):
+    """PLY reader for what the path meets: files written by ``export_ply`` / trimesh / plyfile (binary, float x y z +
+    ``list uchar int vertex_indices``) and, more generally, ascii or binary (either byte order) files whose vertex
+    element carries x, y, z among any scalar properties (normals, colours ... are skipped) and whose face element
+    starts with the index list.  Polygons are fan-triangulated; elements after ``face`` are ignored."""
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    try:
+        end = raw.index(b"end_header")
+        end = raw.index(b"\n", end) + 1
+    except ValueError:
+        raise ValueError(f"{path}: not a PLY file (no end_header)") from None
+    lines = [l.strip() for l in raw[:end].decode("ascii", "replace").splitlines()]
+    if not lines or lines[0] != "ply":
+        raise ValueError(f"{path}: not a PLY file")
+    fmt = next((l.split()[1] for l in lines if l.startswith("format ")), None)
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+        raise ValueError(f"{path}: unknown PLY format {fmt!r}")
+    elements = []                                  # [name, count, [(kind, ...)]]
+    for l in lines:
+        tok = l.split()
+        if not tok:
+            continue
+        if tok[0] == "element":
+            elements.append([tok[1], int(tok[2]), []])
+        elif tok[0] == "property":
+            if not elements:
+                raise ValueError(f"{path}: property before any element")
+            if tok[1] == "list":
+                elements[-1][2].append(("list", _PLY_TYPES[tok[2]], _PLY_TYPES[tok[3]], tok[4]))
+            else:
+                elements[-1][2].append(("scalar", _PLY_TYPES[tok[1]], tok[2]))
+    names = [e[0] for e in elements]
+    if "vertex" not in names:
+        raise ValueError(f"{path}: no vertex element")
+    verts = np.zeros((0, 3), np.float64)
+    faces = np.zeros((0, 3), np.int64)
+    if fmt == "ascii":
+        toks = raw[end:].split()
+        pos = 0
+        for name, count, props in elements:
+            if any(p[0] == "list" for p in props):
+                rows = []
+                for _ in range(count):
+                    row = []
+                    for p in props:
+                        if p[0] == "list":
+                            k = int(toks[pos])
+                            row.append([int(t) for t in toks[pos + 1:pos + 1 + k]])
+                            pos += 1 + k
+                        else:
+                            row.append(None)
+                            pos += 1
+                    rows.append(row)
+                if name == "face":
+                    li = next(i for i, p in enumerate(props) if p[0] == "list")
+                    faces = _fan([r[li] for r in rows])
+            else:
+                block = np.asarray(toks[pos:pos + count * len(props)], dtype=np.float64).reshape(count, len(props))
+                pos += count * len(props)
+                if name == "vertex":
+                    verts = _xyz(path, props, lambda j: block[:, j])
+            if name == "face":
+                break
+        return Mesh(verts, faces)
+    bo = "<" if fmt == "binary_little_endian" else ">"
+    pos = end
+    for name, count, props in elements:
+        if all(p[0] == "scalar" for p in props):
+            dt = np.dtype([(p[2] + "_%d" % j, bo + p[1]) for j, p in enumerate(props)])
+            block = np.frombuffer(raw, dt, count, pos)
+            pos += dt.itemsize * count
+            if name == "vertex":
+                fields = list(dt.names)
+                verts = _xyz(path, props, lambda j: block[fields[j]])
+        else:
+            if name != "face":
+                if "face" in names[names.index(name):]:
+                    raise ValueError(f"{path}: list properties before the face element are not supported")
+                break
+            if props[0][0] != "list":
+                raise ValueError(f"{path}: the face element must start with its index list")
+            _, ct, it, _ = props[0]
+            rest = [p for p in props[1:]]
+            if any(p[0] == "list" for p in rest):
+                raise ValueError(f"{path}: more than one list property per face is not supported")
+            tail = sum(np.dtype(p[1]).itemsize for p in rest)
+            csz, isz = np.dtype(ct).itemsize, np.dtype(it).itemsize
+            rec3 = np.dtype([("n", bo + ct), ("idx", bo + it, (3,)), ("tail", "u1", (tail,))])
+            fast = np.frombuffer(raw, rec3, count, pos) if pos + rec3.itemsize * count <= len(raw) else None
+            if fast is not None and (count == 0 or bool((fast["n"] == 3).all())):
+                faces = fast["idx"].astype(np.int64).reshape(-1, 3)
+            else:                                  # polygons of varying size: walk the records
+                polys = []
+                for _ in range(count):
+                    k = int(np.frombuffer(raw, bo + ct, 1, pos)[0])
+                    polys.append(np.frombuffer(raw, bo + it, k, pos + csz).astype(np.int64).tolist())
+                    pos += csz + k * isz + tail
+                faces = _fan(polys)
+            break
+    return Mesh(verts, faces)
+
+
+def _xyz(path, props, column):
+    cols = {p[2]: j for j, p in enumerate(props)}
+    if not all(k in cols for k in "xyz"):
+        raise ValueError(f"{path}: the vertex element has no x / y / z properties")
+    return np.stack([np.asarray(column(cols[k]), np.float64) for k in "xyz"], 1)
+
+
+def _fan(polys):
+    out = [[p[0], p[k], p[k + 1]] for p in polys for k in range(1, len(p) - 1)]
+    return np.asarray(out, np.int64).reshape(-1, 3)
 
 
 def sample_surface(mesh: Mesh, count, rng=None):

@@ -188,3 +188,66 @@ def _subdivide(v, f, rounds):
             out += [[a, ab, ca], [ab, b, bc], [ca, bc, c], [ab, bc, ca]]
         v, f = np.asarray(v, np.float64), np.asarray(out, np.int64)
     return v, f
+
+
+def test_ply_loader_reads_the_layouts_other_writers_produce(tmp_path):
+    """``trimesh.load`` stand-in: our own files (also empty ones), trimesh-style headers with a comment line, vertex
+    normals / colours between or after x y z, double coordinates, uint index lists, big-endian and ascii files,
+    quads (fan-triangulated), trailing per-face properties and elements after ``face``."""
+    m = _tetra()
+    own = tmp_path / "own.ply"
+    m.export(str(own))
+    back = tl.load(str(own))
+    assert back.vertices.dtype == np.float64 and back.faces.dtype == np.int64
+    assert np.array_equal(back.vertices, m.vertices) and np.array_equal(back.faces, m.faces)
+    tl.export_ply(str(tmp_path / "empty.ply"), np.zeros((0, 3)), np.zeros((0, 3), np.int64))
+    e = tl.load(str(tmp_path / "empty.ply"))
+    assert e.vertices.shape == (0, 3) and e.faces.shape == (0, 3)
+    tl.export_ply(str(tmp_path / "points.ply"), m.vertices, np.zeros((0, 3), np.int64))
+    assert np.array_equal(tl.load(str(tmp_path / "points.ply")).vertices, m.vertices)
+
+    v32 = m.vertices.astype("<f4")
+    nrm = np.arange(12, dtype="<f4").reshape(4, 3)
+    rgba = np.arange(16, dtype=np.uint8).reshape(4, 4)
+    # trimesh-style: comment, normals and colours after the coordinates, uint indices, a per-face colour after the list
+    vrec = np.zeros(4, dtype=[("p", "<f4", (3,)), ("n", "<f4", (3,)), ("c", "u1", (4,))])
+    vrec["p"], vrec["n"], vrec["c"] = v32, nrm, rgba
+    frec = np.zeros(4, dtype=[("k", "u1"), ("i", "<u4", (3,)), ("c", "u1", (3,))])
+    frec["k"], frec["i"] = 3, m.faces
+    head = ("ply\nformat binary_little_endian 1.0\ncomment https://github.com/mikedh/trimesh\nelement vertex 4\n"
+            "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n"
+            "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n"
+            "element face 4\nproperty list uchar uint vertex_indices\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"
+            "element edge 1\nproperty int vertex1\nproperty int vertex2\nend_header\n")
+    with open(tmp_path / "rich.ply", "wb") as fh:
+        fh.write(head.encode() + vrec.tobytes() + frec.tobytes() + np.array([0, 1], "<i4").tobytes())
+    r = tl.load(str(tmp_path / "rich.ply"))
+    assert np.array_equal(r.vertices, v32.astype(np.float64)) and np.array_equal(r.faces, m.faces)
+
+    # big-endian doubles, a quad and a triangle (variable-length records)
+    head = ("ply\nformat binary_big_endian 1.0\nelement vertex 4\nproperty double x\nproperty double y\nproperty double z\n"
+            "element face 2\nproperty list uchar int vertex_index\nend_header\n")
+    body = m.vertices.astype(">f8").tobytes() + b"\x04" + np.array([0, 1, 2, 3], ">i4").tobytes() \
+        + b"\x03" + np.array([0, 2, 1], ">i4").tobytes()
+    with open(tmp_path / "big.ply", "wb") as fh:
+        fh.write(head.encode() + body)
+    b = tl.load(str(tmp_path / "big.ply"))
+    assert np.array_equal(b.vertices, m.vertices) and np.array_equal(b.faces, [[0, 1, 2], [0, 2, 3], [0, 2, 1]])
+
+    # ascii, colours BEFORE the coordinates
+    with open(tmp_path / "ascii.ply", "w") as fh:
+        fh.write("ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 4\nproperty uchar red\nproperty float x\n"
+                 "property float y\nproperty float z\nelement face 3\nproperty list uchar int vertex_indices\nend_header\n")
+        for k, p in enumerate(m.vertices):
+            fh.write("%d %r %r %r\n" % (k, float(p[0]), float(p[1]), float(p[2])))
+        fh.write("3 0 2 1\n4 0 1 3 2\n3 1 2 3\n")
+    a = tl.load(str(tmp_path / "ascii.ply"))
+    assert np.array_equal(a.vertices, m.vertices)
+    assert np.array_equal(a.faces, [[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]])
+
+    for bad, text in (("nohdr.ply", b"ply\nformat ascii 1.0\n"), ("fmt.ply", b"ply\nformat binary_middle_endian 1.0\nend_header\n"),
+                      ("noxyz.ply", b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float a\nend_header\n1\n")):
+        with open(tmp_path / bad, "wb") as fh:
+            fh.write(text)
+        with pytest.raises(ValueError):
+            tl.load(str(tmp_path / bad))
