@@ -10,7 +10,7 @@ GPU, no communication).  This module adds the north star's second mode: grid axi
   pass 2   each rank evaluates its slab of the refit grid
   halo     every rank sends its first plane (both fields) to the rank below it    -> ONE neighbour send / recv
   MC       each rank counts the surface of [z0, z1] (its slab + the neighbour's first plane)
-  sizes    vertex / face counts and the pass-2 flags of every rank -> ONE all_gather of 8 ints, read on the host:
+  sizes    vertex / face counts and the pass-2 flags of every rank -> ONE all_gather of 11 ints, read on the host:
            the only point where a rank waits for its GPU.  If any rank's flags reject the kernel kind in use,
            EVERY rank repeats the sample with the next safer kind (the stitched field never mixes two kinds).
   gather   vertices / faces / global keys go to rank 0 un-padded   -> point-to-point sends of the exact sizes
