@@ -423,3 +423,48 @@ def test_pixel_align_projected_maps_match_reference_golden(name):
     hand, obj = (outs[0][:, 0], outs[1][:, 0]) if topo.kind == "separate" else (outs[0][:, 0], outs[0][:, 1])
     assert np.abs(hand - g["pass1_hand"].reshape(-1)).max() <= 2e-6
     assert np.abs(obj - g["pass1_obj"].reshape(-1)).max() <= 2e-6
+
+
+def test_deep_sdf_package_surface_mirrors_the_reference():
+    """deep_sdf/__init__.py:4-9 star-imports its sub-modules; the names of the path and of its evaluation resolve the
+    same way here (``deep_sdf.create_mesh``, ``deep_sdf.metrics.chamfer.compute_trimesh_chamfer`` of evaluate.py:64 ...)."""
+    import inspect
+    import alignsdf_b200.deep_sdf as deep_sdf
+    for name in ("create_mesh", "convert_sdf_samples_to_ply", "decode_sdf", "ICP_T_S", "compute_trimesh_chamfer",
+                 "procrustes", "procrustes_without_rot", "icp", "transform_points"):
+        assert callable(getattr(deep_sdf, name)), name
+    assert deep_sdf.metrics.chamfer.compute_trimesh_chamfer is deep_sdf.compute_trimesh_chamfer
+    assert deep_sdf.metrics.icp_trans_scale.ICP_T_S is deep_sdf.ICP_T_S
+    # same positional signatures as the reference's functions
+    assert list(inspect.signature(deep_sdf.compute_trimesh_chamfer).parameters)[:4] == \
+        ["gt_mesh_filename", "pred_mesh_filename", "optim", "rot"]
+    assert list(inspect.signature(deep_sdf.create_mesh).parameters)[:5] == ["decoder", "latent_vec", "filename", "N", "max_batch"]
+    assert list(inspect.signature(deep_sdf.decode_sdf).parameters) == ["decoder", "latent_vector", "queries"]
+    assert list(inspect.signature(deep_sdf.icp).parameters) == ["a", "b", "initial", "threshold", "max_iterations", "rot"]
+    assert list(inspect.signature(deep_sdf.procrustes).parameters) == ["a", "b", "reflection", "translation", "scale", "return_cost"]
+    icp = deep_sdf.ICP_T_S
+    for m in ("sample_mesh", "run_icp_f", "run_icp", "get_trans_scale", "export_source_mesh"):
+        assert callable(getattr(icp, m)), m
+    assert list(inspect.signature(icp.run_icp_f).parameters)[1:] == ["max_iter", "stop_error", "stop_improvement", "verbose"]
+
+
+def test_top_level_package_resolves_the_path_functions_like_the_reference_utils_package():
+    """utils/__init__.py:3-4 star-imports utils.mesh and utils.utils: ``utils.<name>`` and ``utils.mesh.<name>`` are the
+    same objects there; same here, with the argument order of the reference's functions."""
+    import inspect
+    import alignsdf_b200 as pkg
+    from alignsdf_b200 import mesh as amesh, utils as autils
+    assert pkg.create_mesh_combined_decoder is amesh.create_mesh_combined_decoder
+    assert pkg.convert_sdf_samples_to_ply is amesh.convert_sdf_samples_to_ply
+    assert pkg.decode_sdf_multi_output is autils.decode_sdf_multi_output
+    assert pkg.kinematic_embedding is autils.kinematic_embedding
+    want = ["hand_branch", "obj_branch", "cls_branch", "decoder", "latent_vec", "mano_results", "obj_results", "cam_intr",
+            "specs", "filename", "N", "max_batch", "offset", "scale", "device", "label_out", "viz", "eval_mode", "task"]
+    assert list(inspect.signature(pkg.create_mesh_combined_decoder).parameters)[:len(want)] == want     # utils/mesh.py:17
+    assert list(inspect.signature(pkg.decode_sdf_multi_output).parameters) == \
+        ["decoder", "latent_vector", "queries", "mano_results", "cam_intr", "specs"]                    # utils/utils.py:561
+    assert list(inspect.signature(pkg.convert_sdf_samples_to_ply).parameters)[:8] == \
+        ["pytorch_3d_sdf_tensor", "voxel_grid_origin", "voxel_size", "ply_filename_out", "offset", "scale", "eval_mode", "task"]
+    assert "create_mesh_combined_decoder" in dir(pkg)
+    with pytest.raises(AttributeError):
+        pkg.no_such_function
